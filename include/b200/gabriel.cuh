@@ -1,0 +1,187 @@
+// Grid solver with Gabriel-graph pruning of the neighbourhood (Delile et al.
+// 2017, Nat. Commun.; Marin-Riera et al. 2016, Bioinformatics): the pair i-j
+// only interacts if no third cell lies inside the sphere whose diameter is
+// gabriel_coefficient * |r_ij| around their midpoint.
+//
+// Reference: compute_cube_gabriel / Gabriel_computer, solvers.cuh:505-644.
+// Included at the end of solvers.cuh. It reuses the grid solver's bucket sort
+// and cube-ordered planes; the kernel itself stays close to the reference's
+// structure (collect candidates, order them by distance with the same
+// selection sort so ties break identically, prune from the far end) because
+// it is used on small sheets only and is not a throughput target.
+#pragma once
+
+namespace yb {
+
+constexpr int GABRIEL_THREADS = 64;
+constexpr int GABRIEL_MAX_NEIGHBOURS = 100;
+
+template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
+    float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
+__global__ void __launch_bounds__(GABRIEL_THREADS) sweep_gabriel(
+    const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
+    const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
+    const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
+    float gabriel_coefficient, Pt* d_dX, float* __restrict__ partials,
+    int stage, int drift_mode, int fix_point, Step_ctl* ctl)
+{
+    using L = Layout<Pt>;
+    __shared__ float s_red[3][GABRIEL_THREADS / 32];
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, GABRIEL_THREADS);
+    float3 cta_sum{0.f, 0.f, 0.f};
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int k = chunk * GABRIEL_THREADS + threadIdx.x;
+        float3 mine{0.f, 0.f, 0.f};
+        if (k < n) {
+            const float4 me = __ldg(pos4 + k);
+            const int my_id = __float_as_int(me.w);
+            const int my_cube = __ldg(cube_sorted + k);
+            const Pt Xi = assemble_pt<Pt>(me, aux + size_t(k) * L::aux_vec4);
+
+            int nb_slot[GABRIEL_MAX_NEIGHBOURS];
+            float nb_dist[GABRIEL_MAX_NEIGHBOURS];
+            int n_nbs = 0;
+
+            // 1. every cell within cube_size, in the reference's sweep order
+            for (int r = 0; r < SWEEP_ROWS; r++) {
+                const long long c = my_cube + (long long)row_shift(r, grid_size);
+                const int lo = __ldg(offset + clamp_cube(c - 1, n_cubes));
+                const int hi = __ldg(offset + clamp_cube(c + 2, n_cubes));
+                for (int q = lo; q < hi; q++) {
+                    const float4 pj = __ldg(pos4 + q);
+                    // r = Xi - Xj lane-wise: x - x', as in operator-
+                    const float dist =
+                        norm3df(me.x - pj.x, me.y - pj.y, me.z - pj.z);
+                    if (dist >= cube_size) continue;
+                    if (n_nbs == GABRIEL_MAX_NEIGHBOURS) continue;
+                    nb_slot[n_nbs] = q;
+                    nb_dist[n_nbs] = dist;
+                    n_nbs++;
+                }
+            }
+
+            // 2. ascending distance (selection sort: same tie-breaking)
+            for (int m = 0; m < n_nbs - 1; m++) {
+                float least = nb_dist[m];
+                int at = m;
+                for (int q = m + 1; q < n_nbs; q++) {
+                    if (nb_dist[q] < least) {
+                        least = nb_dist[q];
+                        at = q;
+                    }
+                }
+                if (at != m) {
+                    const int slot = nb_slot[at];
+                    nb_slot[at] = nb_slot[m];
+                    nb_slot[m] = slot;
+                    nb_dist[at] = nb_dist[m];
+                    nb_dist[m] = least;
+                }
+            }
+
+            // 3. farthest first: keep i-j unless a closer cell sits inside the
+            //    (shrunken) sphere around the midpoint of i and j
+            Pt F{0};
+            float3 sum_v{0.f, 0.f, 0.f};
+            float sum_friction = 0.f;
+            for (int m = n_nbs - 1; m >= 0; m--) {
+                const int kj = nb_slot[m];
+                const float4 pj = __ldg(pos4 + kj);
+                const int j_id = __float_as_int(pj.w);
+                const float4* aux_j = aux + size_t(kj) * L::aux_vec4;
+                const Pt Xj = assemble_pt<Pt>(pj, aux_j);
+                const float dist = nb_dist[m];
+                bool keep = true;
+                if (j_id != my_id) {
+                    const float radius = 0.5f * dist * gabriel_coefficient;
+                    const Pt mid_point = 0.5f * (Xi + Xj);
+                    for (int q = m - 1; q >= 0; q--) {
+                        const float4 pk = __ldg(pos4 + nb_slot[q]);
+                        const float dist_mk = norm3df(mid_point.x - pk.x,
+                            mid_point.y - pk.y, mid_point.z - pk.z);
+                        if (dist_mk < radius) {
+                            keep = false;
+                            break;
+                        }
+                    }
+                }
+                if (!keep) continue;
+                const Pt rij = Xi - Xj;
+                F += pw_int(Xi, rij, dist, my_id, j_id);
+                const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
+                sum_friction += friction;
+                if (friction != 0.f) sum_v += friction * velocity_of<Pt>(aux_j);
+            }
+
+            Pt dX = F;
+            if (SEEDED) {
+                dX = load_pt_rw(d_dX, my_id);
+                dX += F;
+            }
+            if (sum_friction > 0) {
+                dX.x += sum_v.x / sum_friction;
+                dX.y += sum_v.y / sum_friction;
+                dX.z += sum_v.z / sum_friction;
+            }
+            store_pt(d_dX, my_id, dX);
+            mine = float3{dX.x, dX.y, dX.z};
+        }
+        __syncthreads();
+        const float3 chunk_sum =
+            block_sum3<GABRIEL_THREADS>(mine.x, mine.y, mine.z, s_red);
+        cta_sum.x += chunk_sum.x, cta_sum.y += chunk_sum.y, cta_sum.z += chunk_sum.z;
+    }
+    finish_drift<GABRIEL_THREADS>(cta_sum, partials, n, stage, drift_mode,
+        fix_point, d_dX, ctl, s_red);
+}
+
+}  // namespace yb
+
+
+template<typename Pt>
+class Gabriel_computer : public Grid_computer<Pt> {
+public:
+    float gabriel_coefficient;
+
+    Gabriel_computer(int n_max, int grid_size = 50, float cube_size = 1,
+        float gabriel_coefficient = 0.8)
+        : Grid_computer<Pt>{n_max, grid_size, cube_size},
+          gabriel_coefficient{gabriel_coefficient}
+    {}
+
+protected:
+    // both knobs are baked into captured graphs
+    float graph_key() const
+    {
+        return this->cube_size * 4096.f + gabriel_coefficient;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    int prepare()
+    {
+        return 8;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
+        const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
+        int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
+        bool binned_by_predictor)
+    {
+        this->build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
+        const int ctas = this->persistent_ctas(
+            prepare<pw_int, pw_friction, SEEDED>(), yb::GABRIEL_THREADS, max_ctas);
+        yb::sweep_gabriel<Pt, pw_int, pw_friction, SEEDED>
+            <<<ctas, yb::GABRIEL_THREADS, 0, s>>>(d_n, this->n_max, this->pos4,
+                this->aux, this->cube_sorted, this->sort.offset, this->cube_size,
+                this->grid_size, this->n_cubes, gabriel_coefficient, d_dX,
+                d_partials, stage, drift_mode, fix_point, d_ctl);
+    }
+};
+
+template<typename Pt>
+using Gabriel_solver = Heun_solver<Pt, Gabriel_computer>;

@@ -1,0 +1,518 @@
+// Internal: the pairwise-interaction kernels.
+//
+// sweep_cubes  -- Grid solver: for every cell, all cells in the 27 surrounding
+//                 cubes closer than cube_size (reference: compute_cube,
+//                 solvers.cuh:432-463, with add_rhs :147-161 and the zero
+//                 fills :232-234 fused in).
+// sweep_tiles  -- Tile solver: all pairs (reference: compute_tile :286-322).
+//
+// Semantics kept from the reference:
+//  * one thread owns one cell i for the whole sweep, so user functors may
+//    update per-i counters without atomics;
+//  * the functor sees ORIGINAL cell ids and r = Xi - Xj over all lanes of Pt;
+//  * Grid: a pair is handed to the functor iff !(norm3df(r) >= cube_size),
+//    including the self pair (dist == 0), visited in the reference's order:
+//    the 9 (y,z) rows in d_nhood order, ascending slot inside a row -- so the
+//    per-cell sums are accumulated in the same order as the reference's;
+//  * dX[i] (+)= F, then dX.xyz += sum_v / sum_friction if sum_friction > 0.
+//
+// What is different is how the data gets to the ALUs. Cells are physically in
+// cube order (layout.cuh), so for a CTA working on 128 consecutive slots the
+// candidates of each of the 9 rows form ONE contiguous span of pos4[] -- cube
+// ids are linear with x fastest, so cubes c-1, c, c+1 are adjacent, and so are
+// the rows of neighbouring cells. Per chunk the CTA:
+//   1. looks up the 9 spans in offset[] (18 loads for the whole CTA),
+//   2. pulls them into shared memory with 9 cp.async.bulk copies tracked by
+//      one mbarrier (1-D TMA; pos4 records are 16 B so every span is aligned),
+//   3. phase 1: every thread scans its own sub-ranges of the staged spans with
+//      a cheap squared-distance test and appends the survivors to a short
+//      per-thread list in shared memory,
+//   4. phase 2: every thread walks its list: exact norm3df cut-off, functor,
+//      friction. Separating the phases means a warp executes the (expensive,
+//      user-defined) functor for ~max-over-lanes(#neighbours) iterations
+//      instead of ~#candidates -- about 16 instead of 65 in a relaxed tissue.
+// Spans longer than the staging buffer are consumed in several rounds and
+// lists longer than LIST_CAP in several batches; neither changes the order.
+//
+// The kernel is persistent (grid = SMs x resident CTAs, chunks handed out
+// round-robin), so each CTA can keep a running sum of dX for the drift
+// correction; the last CTA to finish adds the per-CTA partials in a fixed
+// order. That replaces thrust::reduce + the device->host copy of
+// solvers.cuh:242 and keeps the result independent of scheduling.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "grid_build.cuh"
+#include "layout.cuh"
+
+namespace yb {
+
+constexpr int SWEEP_THREADS = 128;
+constexpr int SWEEP_STAGE_CAP = 2048;  // staged pos4 records per round (<= 4096)
+constexpr int SWEEP_LIST_CAP = 32;     // neighbour-list entries per batch
+constexpr int SWEEP_ROWS = 9;
+constexpr size_t SWEEP_SMEM =
+    size_t(SWEEP_STAGE_CAP) * sizeof(float4) +
+    size_t(SWEEP_LIST_CAP) * SWEEP_THREADS * sizeof(uint16_t);
+// Squared-distance pre-filter: keep everything the exact test could accept.
+// The rounding error of dx*dx+dy*dy+dz*dz is a few 1e-7 relative; 1e-5 is
+// generous and costs practically no extra list entries.
+constexpr float SWEEP_PREFILTER_SLACK = 1.00001f;
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(arrivals)
+                 : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// global -> shared, 16-byte granular, completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(
+    void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Offset (in cube ids) of neighbour row r = 0..8 relative to a cell's cube.
+// Same ordering as the reference's d_nhood table (solvers.cuh:472-484): the
+// y-shift cycles 0, -1, +1 fastest, the z-shift 0, -1, +1 slowest; inside a row
+// x runs -1, 0, +1, which is simply "the three adjacent ids".
+__device__ __forceinline__ int row_shift(int r, int grid_size)
+{
+    const int ry = r % 3, rz = r / 3;
+    const int dy = ry == 0 ? 0 : (ry == 1 ? -1 : 1);
+    const int dz = rz == 0 ? 0 : (rz == 1 ? -1 : 1);
+    return dy * grid_size + dz * grid_size * grid_size;
+}
+
+__device__ __forceinline__ int clamp_cube(long long c, int n_cubes)
+{
+    return static_cast<int>(c < 0 ? 0 : (c > n_cubes ? n_cubes : c));
+}
+
+template<typename Pt>
+__device__ __forceinline__ Pt assemble_pt(
+    const float4& pos, const float4* __restrict__ aux_of_cell)
+{
+    using L = Layout<Pt>;
+    Pt X;
+    lane(X, 0) = pos.x;
+    lane(X, 1) = pos.y;
+    lane(X, 2) = pos.z;
+    if (L::extras > 0) {
+        float a[L::aux_lanes];
+#pragma unroll
+        for (int q = 0; q < ceil_div(L::extras, 4); q++) {
+            const float4 v = __ldg(aux_of_cell + q);
+            a[4 * q] = v.x, a[4 * q + 1] = v.y;
+            a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int e = 0; e < L::extras; e++) lane(X, 3 + e) = a[e];
+    }
+    return X;
+}
+
+template<typename Pt>
+__device__ __forceinline__ float3 velocity_of(
+    const float4* __restrict__ aux_of_cell)
+{
+    using L = Layout<Pt>;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int l = L::v_lane + c;
+        const float4 q = __ldg(aux_of_cell + l / 4);
+        v[c] = (l % 4 == 0) ? q.x : (l % 4 == 1) ? q.y : (l % 4 == 2) ? q.z : q.w;
+    }
+    return float3{v[0], v[1], v[2]};
+}
+
+// Deterministic CTA-wide sum of three floats; result valid in thread 0.
+template<int THREADS>
+__device__ __forceinline__ float3 block_sum3(
+    float x, float y, float z, float (*s_red)[THREADS / 32])
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, d);
+        y += __shfl_xor_sync(0xffffffffu, y, d);
+        z += __shfl_xor_sync(0xffffffffu, z, d);
+    }
+    const int warp_id = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][warp_id] = x, s_red[1][warp_id] = y, s_red[2][warp_id] = z;
+    }
+    __syncthreads();
+    float3 total{0.f, 0.f, 0.f};
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) {
+            total.x += s_red[0][w], total.y += s_red[1][w], total.z += s_red[2][w];
+        }
+    }
+    return total;
+}
+
+// How the drift of a stage is chosen (Heun_solver::set_fixed*).
+enum Drift_mode : int {
+    DRIFT_MEAN = 0,         // centre of mass stays put
+    DRIFT_POINT = 1,        // one cell stays put
+    DRIFT_POINT_XY_MEAN_Z = 2  // set_fixed_xy, first stage only
+};
+
+// Called by the last CTA of a sweep, after every dX of the stage is written.
+template<typename Pt>
+__device__ __forceinline__ void publish_drift(float3 mean, int mode,
+    int fix_point, const Pt* d_dX, int stage, Step_ctl* ctl)
+{
+    float3 drift = mean;
+    if (mode != DRIFT_MEAN) {
+        const float* p = reinterpret_cast<const float*>(d_dX + fix_point);
+        drift.x = __ldcg(p + 0);
+        drift.y = __ldcg(p + 1);
+        if (mode == DRIFT_POINT) drift.z = __ldcg(p + 2);
+    }
+    ctl->drift[stage][0] = drift.x;
+    ctl->drift[stage][1] = drift.y;
+    ctl->drift[stage][2] = drift.z;
+}
+
+// Last CTA standing: add up the per-CTA partial sums in CTA order and publish
+// the drift for this Heun stage. sum / n follows the reference's operator/=
+// (dtypes.cuh:204-208): multiply by float(1.0 / double(float(n))).
+template<int THREADS, typename Pt>
+__device__ __forceinline__ void finish_drift(float3 my_partial,
+    float* __restrict__ partials, int n, int stage, int drift_mode,
+    int fix_point, const Pt* d_dX, Step_ctl* ctl,
+    float (*s_red)[THREADS / 32])
+{
+    __shared__ bool s_is_last;
+    if (threadIdx.x == 0) {
+        partials[3 * blockIdx.x + 0] = my_partial.x;
+        partials[3 * blockIdx.x + 1] = my_partial.y;
+        partials[3 * blockIdx.x + 2] = my_partial.z;
+        __threadfence();
+        s_is_last = atomicAdd(&ctl->sweep_blocks_done, 1) == int(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int b = threadIdx.x; b < int(gridDim.x); b += THREADS) {
+        x += __ldcg(partials + 3 * b + 0);
+        y += __ldcg(partials + 3 * b + 1);
+        z += __ldcg(partials + 3 * b + 2);
+    }
+    const float3 total = block_sum3<THREADS>(x, y, z, s_red);
+    if (threadIdx.x == 0) {
+        const float inv_n = static_cast<float>(1. / static_cast<float>(n));
+        float3 mean{0.f, 0.f, 0.f};
+        if (n > 0) mean = float3{total.x * inv_n, total.y * inv_n, total.z * inv_n};
+        publish_drift(mean, n > 0 ? drift_mode : DRIFT_MEAN, fix_point, d_dX,
+            stage, ctl);
+        ctl->sweep_blocks_done = 0;
+    }
+}
+
+
+// ---- Grid solver sweep -------------------------------------------------------
+// SEEDED: d_dX already holds the generic forces of this stage and is added to;
+// otherwise d_dX is write-only (no zero fill anywhere).
+template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
+    float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
+    const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
+    const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
+    const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
+    Pt* d_dX, float* __restrict__ partials, int stage, int drift_mode,
+    int fix_point, Step_ctl* ctl)
+{
+    using L = Layout<Pt>;
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    float4* s_pos = reinterpret_cast<float4*>(sweep_smem);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_pos + SWEEP_STAGE_CAP);
+    __shared__ int s_row_lo[SWEEP_ROWS];     // first global slot of row span
+    __shared__ int s_row_v[SWEEP_ROWS + 1];  // start in the concatenated spans
+    __shared__ float s_red[3][SWEEP_THREADS / 32];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int t = threadIdx.x;
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, SWEEP_THREADS);
+    const float reach2 = cube_size * cube_size * SWEEP_PREFILTER_SLACK;
+
+    if (t == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    float3 cta_sum{0.f, 0.f, 0.f};
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int first_slot = chunk * SWEEP_THREADS;
+        const int k = first_slot + t;
+        const bool live = k < n;
+
+        if (t < SWEEP_ROWS) {
+            const int last_slot = min(first_slot + SWEEP_THREADS, n) - 1;
+            const long long shift = row_shift(t, grid_size);
+            const int lo = __ldg(offset +
+                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, n_cubes));
+            const int hi = __ldg(offset +
+                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, n_cubes));
+            s_row_lo[t] = lo;
+            s_row_v[t + 1] = hi > lo ? hi - lo : 0;  // length, scanned below
+        }
+        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+        int my_cube = 0;
+        if (live) {
+            me = __ldg(pos4 + k);
+            my_cube = __ldg(cube_sorted + k);
+        }
+        __syncthreads();
+        if (t == 0) {
+            int v = 0;
+            s_row_v[0] = 0;
+#pragma unroll
+            for (int r = 0; r < SWEEP_ROWS; r++) {
+                v += s_row_v[r + 1];
+                s_row_v[r + 1] = v;
+            }
+        }
+        __syncthreads();
+        const int total = s_row_v[SWEEP_ROWS];
+
+        const int my_id = __float_as_int(me.w);
+        Pt Xi{0};
+        if (live) Xi = assemble_pt<Pt>(me, aux + size_t(k) * L::aux_vec4);
+        Pt F{0};
+        float3 sum_v{0.f, 0.f, 0.f};
+        float sum_friction = 0.f;
+
+        for (int v0 = 0; v0 < total; v0 += SWEEP_STAGE_CAP) {
+            // -- stage the window [v0, v0 + CAP) of the concatenated spans
+            if (v0 > 0) __syncthreads();  // everyone is done with the old window
+            if (t == 0) {
+                const int v1 = min(v0 + SWEEP_STAGE_CAP, total);
+                mbar_expect_tx(&s_bar, uint32_t(v1 - v0) * sizeof(float4));
+#pragma unroll 1
+                for (int r = 0; r < SWEEP_ROWS; r++) {
+                    const int a = max(s_row_v[r], v0);
+                    const int b = min(s_row_v[r + 1], v1);
+                    if (b > a)
+                        bulk_g2s(s_pos + (a - v0),
+                            pos4 + (s_row_lo[r] + (a - s_row_v[r])),
+                            uint32_t(b - a) * sizeof(float4), &s_bar);
+                }
+            }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1u;
+
+            // -- phase 1 + 2, in batches of at most LIST_CAP accepted candidates
+            int r = live ? 0 : SWEEP_ROWS;  // next row to open
+            int a = 0, b = 0;               // current window-relative sub-range
+            bool window_done = false;
+            while (!window_done) {
+                int listed = 0;
+                while (listed < SWEEP_LIST_CAP) {
+                    if (a >= b) {
+                        if (r == SWEEP_ROWS) {
+                            window_done = true;
+                            break;
+                        }
+                        const long long c = my_cube + (long long)row_shift(r, grid_size);
+                        const int lo = __ldg(offset + clamp_cube(c - 1, n_cubes));
+                        const int hi = __ldg(offset + clamp_cube(c + 2, n_cubes));
+                        // to window-relative indices, clipped to the window
+                        const int base = s_row_v[r] - s_row_lo[r] - v0;
+                        a = max(lo + base, 0);
+                        b = min(hi + base, SWEEP_STAGE_CAP);
+                        r++;
+                        // tag = row of this sub-range, for phase 2
+                        continue;
+                    }
+                    const float4 p = s_pos[a];
+                    const float dx = me.x - p.x, dy = me.y - p.y, dz = me.z - p.z;
+                    const float d2 = dx * dx + dy * dy + dz * dz;
+                    if (!(d2 > reach2)) {
+                        s_list[listed * SWEEP_THREADS + t] =
+                            static_cast<uint16_t>(((r - 1) << 12) | a);
+                        listed++;
+                    }
+                    a++;
+                }
+
+                for (int e = 0; e < listed; e++) {
+                    const unsigned entry = s_list[e * SWEEP_THREADS + t];
+                    const int row = entry >> 12, at = entry & 4095;
+                    const float4 pj = s_pos[at];
+                    const int kj = s_row_lo[row] + (v0 + at - s_row_v[row]);
+                    const float4* aux_j = aux + size_t(kj) * L::aux_vec4;
+                    const Pt Xj = assemble_pt<Pt>(pj, aux_j);
+                    const Pt rij = Xi - Xj;
+                    const float dist = norm3df(rij.x, rij.y, rij.z);
+                    if (dist >= cube_size) continue;
+
+                    const int j_id = __float_as_int(pj.w);
+                    F += pw_int(Xi, rij, dist, my_id, j_id);
+                    const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
+                    sum_friction += friction;
+                    if (friction != 0.f)
+                        sum_v += friction * velocity_of<Pt>(aux_j);
+                }
+            }
+        }
+
+        // -- epilogue: dX (+)= F, friction term, drift partial
+        float3 mine{0.f, 0.f, 0.f};
+        if (live) {
+            Pt dX = F;
+            if (SEEDED) {
+                dX = load_pt_rw(d_dX, my_id);
+                dX += F;
+            }
+            if (sum_friction > 0) {
+                dX.x += sum_v.x / sum_friction;
+                dX.y += sum_v.y / sum_friction;
+                dX.z += sum_v.z / sum_friction;
+            }
+            store_pt(d_dX, my_id, dX);
+            mine = float3{dX.x, dX.y, dX.z};
+        }
+        const float3 chunk_sum =
+            block_sum3<SWEEP_THREADS>(mine.x, mine.y, mine.z, s_red);
+        cta_sum.x += chunk_sum.x, cta_sum.y += chunk_sum.y, cta_sum.z += chunk_sum.z;
+    }
+
+    finish_drift<SWEEP_THREADS>(cta_sum, partials, n, stage, drift_mode,
+        fix_point, d_dX, ctl, s_red);
+}
+
+
+// ---- Tile solver sweep -------------------------------------------------------
+// All pairs, self pair included, j ascending -- same order as compute_tile.
+// Tiles of the cube-order-free AoS state are staged to shared memory by the
+// whole CTA (plain loads: n is small wherever the Tile solver is used, and Pt
+// records are only 4-byte aligned, which rules out bulk copies).
+constexpr int TILE_THREADS = 64;
+
+template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
+    float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
+__global__ void __launch_bounds__(TILE_THREADS) sweep_tiles(
+    const int* __restrict__ d_n, int n_max, const Pt* __restrict__ d_X,
+    const float3* __restrict__ d_old_v, Pt* d_dX, float* __restrict__ partials,
+    int stage, int drift_mode, int fix_point, Step_ctl* ctl)
+{
+    using L = Layout<Pt>;
+    __shared__ float s_X[TILE_THREADS * L::lanes];
+    __shared__ float s_v[TILE_THREADS * 3];
+    __shared__ float s_red[3][TILE_THREADS / 32];
+
+    const int t = threadIdx.x;
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, TILE_THREADS);
+    float3 cta_sum{0.f, 0.f, 0.f};
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int i = chunk * TILE_THREADS + t;
+        const bool live = i < n;
+        Pt Xi{0};
+        if (live) Xi = load_pt(d_X, i);
+        Pt F{0};
+        float3 sum_v{0.f, 0.f, 0.f};
+        float sum_friction = 0.f;
+
+        for (int tile_start = 0; tile_start < n; tile_start += TILE_THREADS) {
+            const int in_tile = min(TILE_THREADS, n - tile_start);
+            __syncthreads();
+            // coalesced copy of in_tile AoS records, lane by lane
+            const float* src_X = reinterpret_cast<const float*>(d_X + tile_start);
+            for (int q = t; q < in_tile * L::lanes; q += TILE_THREADS)
+                s_X[q] = __ldg(src_X + q);
+            const float* src_v =
+                reinterpret_cast<const float*>(d_old_v + tile_start);
+            for (int q = t; q < in_tile * 3; q += TILE_THREADS)
+                s_v[q] = __ldg(src_v + q);
+            __syncthreads();
+
+            if (live) {
+                for (int q = 0; q < in_tile; q++) {
+                    Pt Xj;
+#pragma unroll
+                    for (int l = 0; l < L::lanes; l++)
+                        lane(Xj, l) = s_X[q * L::lanes + l];
+                    const int j = tile_start + q;
+                    const Pt rij = Xi - Xj;
+                    const float dist = norm3df(rij.x, rij.y, rij.z);
+                    F += pw_int(Xi, rij, dist, i, j);
+                    const float friction = pw_friction(Xi, rij, dist, i, j);
+                    sum_friction += friction;
+                    if (friction != 0.f)
+                        sum_v += friction *
+                                 float3{s_v[3 * q], s_v[3 * q + 1], s_v[3 * q + 2]};
+                }
+            }
+        }
+
+        float3 mine{0.f, 0.f, 0.f};
+        if (live) {
+            Pt dX = F;
+            if (SEEDED) {
+                dX = load_pt_rw(d_dX, i);
+                dX += F;
+            }
+            if (sum_friction > 0) {
+                dX.x += sum_v.x / sum_friction;
+                dX.y += sum_v.y / sum_friction;
+                dX.z += sum_v.z / sum_friction;
+            }
+            store_pt(d_dX, i, dX);
+            mine = float3{dX.x, dX.y, dX.z};
+        }
+        __syncthreads();
+        const float3 chunk_sum =
+            block_sum3<TILE_THREADS>(mine.x, mine.y, mine.z, s_red);
+        cta_sum.x += chunk_sum.x, cta_sum.y += chunk_sum.y, cta_sum.z += chunk_sum.z;
+    }
+
+    finish_drift<TILE_THREADS>(cta_sum, partials, n, stage, drift_mode,
+        fix_point, d_dX, ctl, s_red);
+}
+
+}  // namespace yb

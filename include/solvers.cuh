@@ -1,0 +1,710 @@
+// Solvers for N-body problems -- B200-native implementation of the ya||a
+// solver API (reference: /root/reference/include/solvers.cuh).
+//
+// The public surface is the reference's: Solution<Pt, Solver>, take_step<pw_int
+// [, pw_friction]>(dt, generic_forces), copy_to_device/host, get_d_n,
+// set_fixed*, Tile_solver / Grid_solver / Gabriel_solver, Grid and d_nhood.
+// A model written for ya||a compiles against this header unchanged. Underneath,
+// a step is a fixed sequence of hand-written sm_100a kernels with no Thrust
+// call, no host synchronisation, no allocation and no device->host copy:
+//
+//   Grid solver, per Heun stage          (kernels: b200/grid_build.cuh,
+//     bin_cells*    cube ids + bucket counts        b200/pair_sweep.cuh,
+//     scan_bins     per-cube offsets                b200/heun.cuh)
+//     place_ids     bucket scatter
+//     reorder_cells state -> cube order (SoA float4 planes)
+//     sweep_cubes   27-cube pairwise sum + friction term + drift reduction
+//     predictor_step / corrector_step   (* stage 2's binning is fused into
+//                                          predictor_step)
+//
+// The cell count is read from d_n on the device, so a step needs nothing from
+// the host; when no generic force is passed, the whole step is captured once
+// as a CUDA graph and replayed.
+#pragma once
+
+#include <assert.h>
+#include <stdlib.h>
+// The solver itself does not use Thrust. These four headers are included only
+// because ya||a models call thrust::fill / thrust::reduce in their own code and
+// rely on solvers.cuh to have pulled them in (reference: solvers.cuh:5-8).
+#include <thrust/execution_policy.h>
+#include <thrust/fill.h>
+#include <thrust/reduce.h>
+#include <thrust/sort.h>
+#include <functional>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "cudebug.cuh"
+#include "dtypes.cuh"
+
+#include "b200/grid_build.cuh"
+#include "b200/heun.cuh"
+#include "b200/layout.cuh"
+#include "b200/pair_sweep.cuh"
+
+#define YALLA_B200 1
+
+
+// ---- user-supplied pieces -------------------------------------------------------
+// A pairwise interaction returns the contribution of j to dXi/dt, given
+// r = Xi - Xj (all members of Pt) and dist = |r.xyz|. i and j are cell ids in
+// the user's arrays (reference: solvers.cuh:15-19).
+template<typename Pt>
+using Pairwise_interaction = Pt(Pt Xi, Pt r, float dist, int i, int j);
+
+// A pairwise friction coefficient weights the neighbour's previous velocity in
+// v_i = F_i + <v_j(t - dt)>, see http://dx.doi.org/10.1007/s10237-014-0613-5.
+template<typename Pt>
+using Pairwise_friction = float(Pt Xi, Pt r, float dist, int i, int j);
+
+// Default: neighbours closer than 1 drag on each other.
+template<typename Pt>
+__device__ float friction_w_neighbour(Pt Xi, Pt r, float dist, int i, int j)
+{
+    return (i != j && dist < 1) ? 1.f : 0.f;
+}
+
+// No neighbour friction: cells only feel the (implicit) background.
+template<typename Pt>
+__device__ float friction_on_background(Pt Xi, Pt r, float dist, int i, int j)
+{
+    return 0;
+}
+
+// Generic forces are host callables invoked once per Heun stage with the stage's
+// positions and the (zeroed) derivative array, BEFORE the pairwise sweep adds to
+// it -- e.g. link_forces, or a reset of neighbour counters.
+// This is std::function<void(int n, const Pt* d_X, Pt* d_dX)> like the
+// reference's alias (solvers.cuh:44-46), plus a converting constructor for the
+// older two-argument form (d_X, d_dX) that the upstream tests still use.
+template<typename Pt>
+class Generic_forces
+    : public std::function<void(const int, const Pt*, Pt*)> {
+    using Base = std::function<void(const int, const Pt*, Pt*)>;
+
+public:
+    using Base::Base;
+    Generic_forces() = default;
+
+    template<typename F,
+        typename = decltype(std::declval<F&>()(
+            static_cast<const Pt*>(nullptr), static_cast<Pt*>(nullptr)))>
+    Generic_forces(F two_argument_form)
+        : Base([two_argument_form](const int, const Pt* d_X,
+                   Pt* d_dX) mutable { two_argument_form(d_X, d_dX); })
+    {}
+};
+
+template<typename Pt>
+void no_gen_forces(const int n, const Pt* __restrict__ d_X, Pt* d_dX)
+{}
+
+
+namespace yb {
+
+// True if the callable is exactly no_gen_forces<Pt>: then nothing seeds dX and
+// the step can run from a captured graph.
+template<typename Pt>
+bool is_no_gen_forces(const Generic_forces<Pt>& f)
+{
+    using Fn = void (*)(const int, const Pt*, Pt*);
+    const Fn* target = f.template target<Fn>();
+    return target != nullptr && *target == &no_gen_forces<Pt>;
+}
+
+inline bool graphs_enabled()
+{
+    static bool enabled = [] {
+        const char* v = getenv("YALLA_B200_NO_GRAPH");
+        return !(v && v[0] && v[0] != '0');
+    }();
+    return enabled;
+}
+
+// A captured Heun step. Kernel arguments are baked into the graph, so it is
+// keyed by everything the host passes by value.
+struct Step_graph {
+    const void* instantiation;  // identifies take_step<pw_int, pw_friction>
+    float dt, cube_size;
+    int mode0, mode1, fix_point;
+    cudaGraphExec_t exec;
+};
+
+}  // namespace yb
+
+
+// Solution<Pt, Solver> combines a method, Solver, with a point type, Pt. It
+// owns the host copy of the state and exposes the device arrays the solver
+// integrates (reference: solvers.cuh:56-106).
+template<typename Pt, template<typename> class Solver>
+class Solution : public Solver<Pt> {
+public:
+    Pt* h_X;                                      // State on the host
+    Pt* const d_X = Solver<Pt>::d_X;              // State on the device
+    float3* const d_old_v = Solver<Pt>::d_old_v;  // Velocities of the last step
+    int* const h_n = (int*)malloc(sizeof(int));   // Number of cells
+    int* const d_n = Solver<Pt>::d_n;
+    const int n_max;
+
+    template<typename... Args>
+    Solution(int n_max, Args... args)
+        : Solver<Pt>{n_max, args...}, n_max{n_max}
+    {
+        *h_n = n_max;
+        // Pinned, so that copies run at full PCIe rate; plain malloc if the
+        // host cannot pin that much.
+        const size_t bytes = static_cast<size_t>(n_max) * sizeof(Pt);
+        if (cudaMallocHost(&h_X, bytes) == cudaSuccess) {
+            h_X_pinned = true;
+        } else {
+            cudaGetLastError();
+            h_X = static_cast<Pt*>(malloc(bytes));
+        }
+    }
+    Solution(const Solution&) = delete;
+    Solution& operator=(const Solution&) = delete;
+    ~Solution()
+    {
+        if (h_X_pinned)
+            cudaFreeHost(h_X);
+        else
+            free(h_X);
+        free(h_n);
+    }
+
+    // Both copies move all n_max elements plus n and block, as in the reference.
+    void copy_to_device()
+    {
+        assert(*h_n <= n_max);
+        YB_CUDA(cudaMemcpy(d_X, h_X, static_cast<size_t>(n_max) * sizeof(Pt),
+            cudaMemcpyHostToDevice));
+        YB_CUDA(cudaMemcpy(d_n, h_n, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    void copy_to_host()
+    {
+        YB_CUDA(cudaMemcpy(h_X, d_X, static_cast<size_t>(n_max) * sizeof(Pt),
+            cudaMemcpyDeviceToHost));
+        YB_CUDA(cudaMemcpy(h_n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
+        assert(*h_n <= n_max);
+    }
+    int get_d_n() { return Solver<Pt>::get_d_n(); }
+
+    template<Pairwise_interaction<Pt> pw_int>
+    void take_step(float dt, Generic_forces<Pt> gen_forces = no_gen_forces<Pt>)
+    {
+        Solver<Pt>::template take_step<pw_int, friction_w_neighbour<Pt>>(
+            dt, gen_forces);
+    }
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
+    void take_step(float dt, Generic_forces<Pt> gen_forces = no_gen_forces<Pt>)
+    {
+        Solver<Pt>::template take_step<pw_int, pw_friction>(dt, gen_forces);
+    }
+
+private:
+    bool h_X_pinned = false;
+};
+
+
+// 2nd order solver for the equation v = F + <v(t - dt)> for x, y, and z, where
+// <v> is the mean velocity of the neighbours weighted by the friction
+// coefficients. One point or the centre of mass is kept fixed. Solves
+// dw/dt = F_w for the other members of Pt (reference: solvers.cuh:109-276).
+// Computer says how the pairwise sums are formed.
+template<typename Pt, template<typename> class Computer>
+class Heun_solver : public Computer<Pt> {
+public:
+    template<typename... Args>
+    Heun_solver(int n_max, Args... args)
+        : Computer<Pt>{n_max, args...}, n_max{n_max}
+    {
+        const size_t cells = static_cast<size_t>(n_max > 0 ? n_max : 1);
+        YB_CUDA(cudaMalloc(&d_X, cells * sizeof(Pt)));
+        YB_CUDA(cudaMalloc(&d_dX, cells * sizeof(Pt)));
+        YB_CUDA(cudaMalloc(&d_X1, cells * sizeof(Pt)));
+        YB_CUDA(cudaMalloc(&d_dX1, cells * sizeof(Pt)));
+        YB_CUDA(cudaMalloc(&d_old_v, cells * sizeof(float3)));
+        YB_CUDA(cudaMemset(d_old_v, 0, cells * sizeof(float3)));
+        YB_CUDA(cudaMalloc(&d_n, sizeof(int)));
+        YB_CUDA(cudaMemset(d_n, 0, sizeof(int)));
+
+        YB_CUDA(cudaMalloc(&d_ctl, sizeof(yb::Step_ctl)));
+        yb::Step_ctl fresh{};
+        fresh.scan_epoch = 1;
+        YB_CUDA(cudaMemcpy(
+            d_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        max_sweep_ctas = yb::sm_count() * 16;
+        YB_CUDA(cudaMalloc(&d_partials, 3 * max_sweep_ctas * sizeof(float)));
+        YB_CUDA(cudaStreamCreateWithFlags(
+            &capture_stream, cudaStreamNonBlocking));
+    }
+    Heun_solver(const Heun_solver&) = delete;
+    Heun_solver& operator=(const Heun_solver&) = delete;
+    ~Heun_solver()
+    {
+        cudaStreamSynchronize(stream);
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        cudaStreamDestroy(capture_stream);
+        cudaFree(d_partials);
+        cudaFree(d_ctl);
+        cudaFree(d_n);
+        cudaFree(d_old_v);
+        cudaFree(d_dX1);
+        cudaFree(d_X1);
+        cudaFree(d_dX);
+        cudaFree(d_X);
+    }
+
+    // Keep the centre of mass fixed (default) ...
+    void set_fixed() { fix_com = true; }
+    // ... or one cell ...
+    void set_fixed(int point_id)
+    {
+        fix_com = false;
+        fix_point = point_id;
+    }
+    // ... or one cell in x and y, and the centre of mass in z.
+    void set_fixed_xy(int point_id)
+    {
+        fix_com = false;
+        fix_com_z = true;
+        fix_point = point_id;
+    }
+
+    // Extension: number of cells whose cube id fell outside the grid so far
+    // (the reference asserts on the device instead). Blocks.
+    int cells_out_of_grid()
+    {
+        yb::Step_ctl snapshot;
+        YB_CUDA(cudaMemcpy(
+            &snapshot, d_ctl, sizeof(snapshot), cudaMemcpyDeviceToHost));
+        return snapshot.out_of_grid;
+    }
+
+    // Extension: all solver work is issued to this stream (default: the legacy
+    // default stream, like every launch in a ya||a model).
+    cudaStream_t stream = 0;
+
+protected:
+    Pt *d_X, *d_dX, *d_X1, *d_dX1;
+    float3* d_old_v;
+    int* d_n;
+    bool fix_com = true;
+    bool fix_com_z = false;
+    int fix_point = 0;
+    const int n_max;
+
+    int get_d_n()
+    {
+        int n;
+        YB_CUDA(cudaMemcpyAsync(
+            &n, d_n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        YB_CUDA(cudaStreamSynchronize(stream));
+        assert(n <= n_max);
+        return n;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
+    void take_step(float dt, Generic_forces<Pt> gen_forces)
+    {
+        // Drift selection per stage, exactly as solvers.cuh:241-253, :266-272.
+        const int mode0 =
+            (fix_com || fix_com_z)
+                ? (fix_com_z ? yb::DRIFT_POINT_XY_MEAN_Z : yb::DRIFT_MEAN)
+                : yb::DRIFT_POINT;
+        const int mode1 = fix_com ? yb::DRIFT_MEAN : yb::DRIFT_POINT;
+
+        if (!yb::is_no_gen_forces(gen_forces)) {
+            // The callback is arbitrary host code that needs n: one blocking
+            // read of d_n, then the stage kernels are issued directly.
+            const int n = get_d_n();
+            enqueue_stage<pw_int, pw_friction, true>(
+                stream, 0, dt, mode0, n, gen_forces);
+            enqueue_stage<pw_int, pw_friction, true>(
+                stream, 1, dt, mode1, n, gen_forces);
+            return;
+        }
+
+        Generic_forces<Pt> none;
+        if (!yb::graphs_enabled()) {
+            enqueue_stage<pw_int, pw_friction, false>(
+                stream, 0, dt, mode0, 0, none);
+            enqueue_stage<pw_int, pw_friction, false>(
+                stream, 1, dt, mode1, 0, none);
+            return;
+        }
+
+        static const char instantiation_tag = 0;
+        const float cube_size = Computer<Pt>::graph_key();
+        // occupancy queries and attribute changes must not happen mid-capture
+        Computer<Pt>::template prepare<pw_int, pw_friction, false>();
+        for (auto& g : graphs) {
+            if (g.instantiation == &instantiation_tag && g.dt == dt &&
+                g.cube_size == cube_size && g.mode0 == mode0 &&
+                g.mode1 == mode1 && g.fix_point == fix_point) {
+                YB_CUDA(cudaGraphLaunch(g.exec, stream));
+                return;
+            }
+        }
+        cudaGraph_t graph;
+        YB_CUDA(cudaStreamBeginCapture(
+            capture_stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_stage<pw_int, pw_friction, false>(
+            capture_stream, 0, dt, mode0, 0, none);
+        enqueue_stage<pw_int, pw_friction, false>(
+            capture_stream, 1, dt, mode1, 0, none);
+        YB_CUDA(cudaStreamEndCapture(capture_stream, &graph));
+        yb::Step_graph entry{&instantiation_tag, dt, cube_size, mode0, mode1,
+            fix_point, nullptr};
+        YB_CUDA(cudaGraphInstantiate(&entry.exec, graph, 0));
+        YB_CUDA(cudaGraphDestroy(graph));
+        graphs.push_back(entry);
+        YB_CUDA(cudaGraphLaunch(entry.exec, stream));
+    }
+
+private:
+    yb::Step_ctl* d_ctl;
+    float* d_partials;
+    int max_sweep_ctas;
+    cudaStream_t capture_stream;
+    std::vector<yb::Step_graph> graphs;
+
+    // One Heun stage: [seed dX with generic forces] -> pairwise sweep (writes
+    // dX or dX1 and the stage's drift) -> predictor or corrector update.
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void enqueue_stage(cudaStream_t s, int stage, float dt, int drift_mode,
+        int n, Generic_forces<Pt>& gen_forces)
+    {
+        const Pt* X_stage = stage == 0 ? d_X : d_X1;
+        Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
+        if (SEEDED) {
+            YB_CUDA(cudaMemsetAsync(
+                dX_stage, 0, static_cast<size_t>(n) * sizeof(Pt), s));
+            // lets link_forces & co. see the cell count and the stream
+            yb::Stage_context context{n, n_max, s};
+            yb::current_stage() = &context;
+            gen_forces(n, X_stage, dX_stage);
+            yb::current_stage() = nullptr;
+        }
+        const bool binned_by_predictor = stage == 1;
+        Computer<Pt>::template pwints<pw_int, pw_friction, SEEDED>(s, d_n,
+            X_stage, d_old_v, dX_stage, d_partials, max_sweep_ctas, stage,
+            drift_mode, fix_point, d_ctl, binned_by_predictor);
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        if (stage == 0) {
+            Computer<Pt>::predict(s, blocks, d_n, dt, d_X, d_dX, d_X1, d_ctl);
+        } else {
+            yb::corrector_step<Pt><<<blocks, 256, 0, s>>>(
+                d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+        }
+        YB_CUDA(cudaGetLastError());
+    }
+};
+
+
+// ---- all pairs ---------------------------------------------------------------------
+// Kept for mesh.cuh and user code that sizes launches with it.
+const auto TILE_SIZE = 32;
+
+template<typename Pt>
+class Tile_computer {
+public:
+    Tile_computer(int n_max) : n_max{n_max} {}
+
+protected:
+    float graph_key() const { return 0.f; }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void prepare()
+    {}
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
+        const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
+        int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
+        bool /*binned_by_predictor*/)
+    {
+        int blocks = yb::ceil_div(n_max > 0 ? n_max : 1, yb::TILE_THREADS);
+        if (blocks > max_ctas) blocks = max_ctas;
+        yb::sweep_tiles<Pt, pw_int, pw_friction, SEEDED>
+            <<<blocks, yb::TILE_THREADS, 0, s>>>(d_n, n_max, d_X, d_old_v, d_dX,
+                d_partials, stage, drift_mode, fix_point, d_ctl);
+    }
+
+    void predict(cudaStream_t s, int blocks, const int* d_n, float dt,
+        const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
+    {
+        yb::predictor_step<Pt, false><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
+            d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+    }
+
+private:
+    const int n_max;
+};
+
+template<typename Pt>
+using Tile_solver = Heun_solver<Pt, Tile_computer>;
+
+
+// ---- neighbour grid ----------------------------------------------------------------
+// Offsets from a cube to its 27 neighbours (x fastest, then y, then z; within
+// each: -1, 0, +1 resp. 0, -, +), filled in by the grid solvers' constructors.
+// User kernels that pick random neighbour cubes read it (reference :428).
+__constant__ int d_nhood[27];
+
+namespace yb {
+inline void upload_nhood(int grid_size)
+{
+    int h_nhood[27];
+    const int step[3] = {0, -1, 1};
+    for (int z = 0; z < 3; z++)
+        for (int y = 0; y < 3; y++)
+            for (int x = 0; x < 3; x++)
+                h_nhood[9 * z + 3 * y + x] = (x - 1) + step[y] * grid_size +
+                                             step[z] * grid_size * grid_size;
+    YB_CUDA(cudaMemcpyToSymbol(d_nhood, h_nhood, sizeof(h_nhood)));
+}
+
+// Scratch shared by the public Grid and the grid solvers: the bucket sort.
+struct Bucket_sort {
+    int* key = nullptr;       // cube id per cell, original order
+    int* arrival = nullptr;   // arrival rank within the cube
+    int* slot_id = nullptr;   // cell id per slot, arrival order within cubes
+    int* count = nullptr;     // per cube, zero between builds
+    int* offset = nullptr;    // exclusive prefix sum, n_cubes + 1 (+ padding)
+    unsigned long long* status = nullptr;  // look-back words of the scan
+    int n_tiles = 0;
+
+    void allocate(int n_max, int n_cubes)
+    {
+        const size_t cells = static_cast<size_t>(n_max > 0 ? n_max : 1);
+        const size_t bins = static_cast<size_t>(scan_padded(n_cubes + 1));
+        n_tiles = static_cast<int>(bins / SCAN_TILE);
+        YB_CUDA(cudaMalloc(&key, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&arrival, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&slot_id, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&count, bins * sizeof(int)));
+        YB_CUDA(cudaMemset(count, 0, bins * sizeof(int)));
+        YB_CUDA(cudaMalloc(&offset, bins * sizeof(int)));
+        YB_CUDA(cudaMemset(offset, 0, bins * sizeof(int)));
+        YB_CUDA(cudaMalloc(&status, n_tiles * sizeof(unsigned long long)));
+        YB_CUDA(cudaMemset(status, 0, n_tiles * sizeof(unsigned long long)));
+    }
+    void release()
+    {
+        cudaFree(status);
+        cudaFree(offset);
+        cudaFree(count);
+        cudaFree(slot_id);
+        cudaFree(arrival);
+        cudaFree(key);
+    }
+};
+}  // namespace yb
+
+
+// Stand-alone neighbour grid for user kernels (e.g. protrusion updates pick
+// random cells from neighbouring cubes). After build():
+//   d_cube_id[k]   cube id of sorted slot k (ascending)
+//   d_point_id[k]  original cell id in slot k (ascending inside a cube)
+//   d_cube_start[c], d_cube_end[c]  inclusive slot range of cube c, or -1, -2
+// bit-identical to the reference's arrays (solvers.cuh:380-425).
+class Grid {
+public:
+    int *d_cube_id, *d_point_id, *d_cube_start, *d_cube_end;
+    Grid* d_grid;
+    const int n_max, grid_size, n_cubes;
+
+    Grid(int n_max, int gs = 50)
+        : n_max{n_max}, grid_size{gs}, n_cubes{gs * gs * gs}
+    {
+        const size_t cells = static_cast<size_t>(n_max > 0 ? n_max : 1);
+        YB_CUDA(cudaMalloc(&d_cube_id, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&d_point_id, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&d_cube_start, n_cubes * sizeof(int)));
+        YB_CUDA(cudaMalloc(&d_cube_end, n_cubes * sizeof(int)));
+        sort.allocate(n_max, n_cubes);
+        YB_CUDA(cudaMalloc(&d_ctl, sizeof(yb::Step_ctl)));
+        yb::Step_ctl fresh{};
+        fresh.scan_epoch = 1;
+        YB_CUDA(cudaMemcpy(
+            d_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        YB_CUDA(cudaMalloc(&d_n_scratch, sizeof(int)));
+
+        YB_CUDA(cudaMalloc(&d_grid, sizeof(Grid)));
+        YB_CUDA(cudaMemcpy(d_grid, this, sizeof(Grid), cudaMemcpyHostToDevice));
+    }
+    Grid(const Grid&) = delete;
+    Grid& operator=(const Grid&) = delete;
+    ~Grid()
+    {
+        cudaFree(d_grid);
+        cudaFree(d_n_scratch);
+        cudaFree(d_ctl);
+        sort.release();
+        cudaFree(d_cube_end);
+        cudaFree(d_cube_start);
+        cudaFree(d_point_id);
+        cudaFree(d_cube_id);
+    }
+
+    template<typename Pt>
+    void build(
+        const int n, const Pt* __restrict__ d_X, const float cube_size = 1)
+    {
+        assert(n <= n_max);
+        const cudaStream_t s = 0;
+        const int sms = yb::sm_count();
+        YB_CUDA(cudaMemcpyAsync(
+            d_n_scratch, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+        yb::fill_cube_ranges<<<yb::stride_grid(n_cubes, 256, sms), 256, 0, s>>>(
+            n_cubes, d_cube_start, d_cube_end);
+        if (n > 0) {
+            const int blocks = yb::stride_grid(n, 256, sms);
+            yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n_scratch, n_max, d_X,
+                cube_size, grid_size, n_cubes, sort.key, sort.arrival,
+                sort.count, d_ctl);
+            yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
+                sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
+            yb::place_ids<<<blocks, 256, 0, s>>>(d_n_scratch, n_max, sort.key,
+                sort.arrival, sort.offset, sort.slot_id);
+            yb::publish_grid<<<blocks, 256, 0, s>>>(n, sort.key, sort.offset,
+                sort.slot_id, d_cube_id, d_point_id, d_cube_start, d_cube_end);
+        }
+        YB_CUDA(cudaGetLastError());
+    }
+    template<typename Pt, template<typename> class Solver>
+    void build(Solution<Pt, Solver>& points, const float cube_size = 1)
+    {
+        auto n = points.get_d_n();
+        assert(n <= n_max);
+        build(n, points.d_X, cube_size);
+    }
+
+private:
+    yb::Bucket_sort sort;
+    yb::Step_ctl* d_ctl;
+    int* d_n_scratch;
+};
+
+
+// Pairwise sums over the 27 neighbouring cubes ONLY for cells closer than
+// cube_size; scales linearly in n (reference: Grid_computer, :465-499).
+template<typename Pt>
+class Grid_computer {
+public:
+    float cube_size;  // may be changed between steps
+
+    Grid_computer(int n_max, int grid_size = 50, float cube_size = 1)
+        : cube_size{cube_size}, n_max{n_max}, grid_size{grid_size},
+          n_cubes{grid_size * grid_size * grid_size}
+    {
+        yb::upload_nhood(grid_size);
+        sort.allocate(n_max, n_cubes);
+        const size_t cells = static_cast<size_t>(n_max > 0 ? n_max : 1);
+        YB_CUDA(cudaMalloc(&pos4, cells * sizeof(float4)));
+        YB_CUDA(cudaMalloc(
+            &aux, cells * yb::Layout<Pt>::aux_vec4 * sizeof(float4)));
+        YB_CUDA(cudaMalloc(&cube_sorted, cells * sizeof(int)));
+    }
+    Grid_computer(const Grid_computer&) = delete;
+    Grid_computer& operator=(const Grid_computer&) = delete;
+    ~Grid_computer()
+    {
+        cudaFree(cube_sorted);
+        cudaFree(aux);
+        cudaFree(pos4);
+        sort.release();
+    }
+
+protected:
+    float graph_key() const { return cube_size; }
+
+    // Resident CTAs per SM of a persistent sweep kernel (queried once).
+    template<typename Kernel>
+    static int resident_ctas(Kernel kernel, int threads, size_t smem)
+    {
+        YB_CUDA(cudaFuncSetAttribute(kernel,
+            cudaFuncAttributePreferredSharedMemoryCarveout,
+            cudaSharedmemCarveoutMaxShared));
+        int resident = 0;
+        YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &resident, kernel, threads, smem));
+        return resident > 0 ? resident : 1;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    int prepare()
+    {
+        static const int ctas_per_sm =
+            resident_ctas(yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>,
+                yb::SWEEP_THREADS, yb::SWEEP_SMEM);
+        return ctas_per_sm;
+    }
+
+    // Cube ids -> bucket sort -> state in cube order (b200/grid_build.cuh).
+    void build_index(cudaStream_t s, const int* d_n, const Pt* d_X,
+        const float3* d_old_v, yb::Step_ctl* d_ctl, bool binned_by_predictor)
+    {
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        if (!binned_by_predictor)
+            yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, cube_size,
+                grid_size, n_cubes, sort.key, sort.arrival, sort.count, d_ctl);
+        yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
+            sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
+        yb::place_ids<<<blocks, 256, 0, s>>>(
+            d_n, n_max, sort.key, sort.arrival, sort.offset, sort.slot_id);
+        yb::reorder_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, d_old_v,
+            sort.key, sort.offset, sort.slot_id, pos4, aux, cube_sorted);
+    }
+
+    int persistent_ctas(int ctas_per_sm, int threads, int max_ctas) const
+    {
+        int ctas = yb::sm_count() * ctas_per_sm;
+        const int chunks = yb::ceil_div(n_max > 0 ? n_max : 1, threads);
+        if (ctas > chunks) ctas = chunks;
+        if (ctas > max_ctas) ctas = max_ctas;
+        return ctas;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
+        const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
+        int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
+        bool binned_by_predictor)
+    {
+        build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
+        const int ctas = persistent_ctas(
+            prepare<pw_int, pw_friction, SEEDED>(), yb::SWEEP_THREADS, max_ctas);
+        yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
+            <<<ctas, yb::SWEEP_THREADS, yb::SWEEP_SMEM, s>>>(d_n, n_max, pos4,
+                aux, cube_sorted, sort.offset, cube_size, grid_size, n_cubes,
+                d_dX, d_partials, stage, drift_mode, fix_point, d_ctl);
+    }
+
+    void predict(cudaStream_t s, int blocks, const int* d_n, float dt,
+        const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
+    {
+        yb::predictor_step<Pt, true><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
+            d_dX, d_X1, d_ctl, cube_size, grid_size, n_cubes, sort.key,
+            sort.arrival, sort.count);
+    }
+
+    yb::Bucket_sort sort;
+    float4* pos4;
+    float4* aux;
+    int* cube_sorted;
+    const int n_max, grid_size, n_cubes;
+};
+
+template<typename Pt>
+using Grid_solver = Heun_solver<Pt, Grid_computer>;
+
+#include "b200/gabriel.cuh"
