@@ -1,0 +1,147 @@
+/* C ABI of the ya||a hot path: grid build, link forces and whole model steps.
+ *
+ * ya||a itself has no FFI: a model is a .cu file that instantiates
+ * Solution<Pt, Solver>::take_step<pairwise_fn> (reference include/solvers.cuh:
+ * 60-106, 226-275), so the pairwise interaction is compiled INTO the force
+ * kernel. The drop-in boundary for user models is therefore the header set in
+ * this directory (solvers.cuh, links.cuh, ...). This C ABI is the second
+ * boundary: it exposes the path for fixed, named models ("plugins") with plain
+ * pointers and sizes, so that a host program in any language -- here the Python
+ * test-suite and bench.py through ctypes -- can drive it, and so that the SAME
+ * entry points can be served by three interchangeable libraries:
+ *
+ *   yalla_b200/_lib/libyalla_b200.so   this repo's headers        (the product)
+ *   oracle/_ref/libyalla_ref.so        the unmodified reference headers,
+ *                                      compiled from /root/reference (GPU)
+ *   oracle/_build/libyalla_oracle.so   the CPU restatement in oracle/ (tests
+ *                                      and cpu_baseline only)
+ *
+ * The first two are built from the one source yalla_b200/csrc/capi.cu, which
+ * uses nothing but the public ya||a API -- that it compiles against both header
+ * sets is the API-compatibility check.
+ *
+ * Conventions: every function returns 0 on success and a negative YB_E* code
+ * otherwise; yb_last_error() describes the last failure of the calling
+ * thread. State is array-of-structs float32: `lanes` floats per cell in the
+ * member order of the model's point type (x, y, z, then extras). Pointers
+ * named h_* are host memory, d_* device memory. Nothing here synchronises the
+ * device unless it says so.
+ */
+#ifndef YALLA_B200_H
+#define YALLA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_OK 0
+#define YB_EINVAL -1   /* bad argument (unknown model, n > n_max, ...)     */
+#define YB_ECUDA -2    /* a CUDA call failed                                */
+#define YB_ENOSYS -3   /* not available in this library (e.g. GPU entry in
+                          the CPU oracle)                                   */
+
+typedef struct yb_sim yb_sim;
+
+/* "yalla-b200", "yalla-reference" or "yalla-oracle", plus build details. */
+const char* yb_build_info(void);
+const char* yb_last_error(void);
+
+/* ---- whole-model steps ---------------------------------------------------
+ * Each model is one Solution<Pt, Solver> plus the user code of a reference
+ * example; one "step" is what that example does per iteration on the device
+ * (take_step, and for growing models the division kernel) -- no host I/O.
+ *
+ *  name           Pt (lanes)  solver  follows
+ *  "springs"      float3 (3)  Tile    examples/springs.cu:14-21 (L0 = 0.5)
+ *  "spring_tile"  float3 (3)  Tile    tests/test_solvers.cu:44-53 clipped_spring
+ *  "spring_grid"  float3 (3)  Grid    the same, Grid_solver
+ *  "relu_tile"    float3 (3)  Tile    include/inits.cuh:78-93 relu_force
+ *  "relu_grid"    float3 (3)  Grid    the same, Grid_solver
+ *  "epithelium"   Po_cell (5) Grid    examples/epithelium.cu:16-31 layer_force,
+ *                                     friction_on_background
+ *  "growth"       Po_cell (5) Grid    examples/passive_growth.cu: relu_w_epithelium
+ *                                     :29-57, reset_nbs :107-113, proliferate
+ *                                     :59-91 (curand, dynamic n)
+ *  "protrusions"  float3 (3)  Grid    examples/sorting_prot.cu-style Links +
+ *                                     link_forces as generic force, relu_force
+ *  "branching"    Cell (7)    Grid    examples/branching.cu:57-110
+ *                                     epi_turing_mes_noturing + counters
+ *
+ * grid_size / cube_size are the Grid_solver constructor arguments
+ * (solvers.cuh:469) and are ignored by Tile models. */
+int yb_sim_create(const char* model, int n_max, int grid_size,
+    float cube_size, yb_sim** out);
+void yb_sim_destroy(yb_sim* sim);
+int yb_sim_lanes(const yb_sim* sim);
+int yb_sim_n_max(const yb_sim* sim);
+
+/* Model parameters by name (e.g. "prolif_rate", "mean_dist", "seed",
+ * "link_strength", "fix_point"); must be set before the first step that uses
+ * them. Unknown names return YB_EINVAL. */
+int yb_sim_set_param(yb_sim* sim, const char* name, double value);
+
+/* Host <-> device, blocking: Solution::copy_to_device / copy_to_host
+ * (solvers.cuh:80-91) restricted to the first n cells of the caller's
+ * buffer. set_state also resets old velocities to zero when reset_v != 0. */
+int yb_sim_set_state(yb_sim* sim, const float* h_X, int n, int reset_v);
+int yb_sim_get_state(yb_sim* sim, float* h_X, int capacity, int* n_out);
+int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity);
+
+/* Integer per-cell properties of the model by name ("type", "mes_nbs",
+ * "epi_nbs", ...): Property<int>::copy_to_device / copy_to_host. */
+int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n);
+int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity);
+
+/* Links of models that have them: pairs (a, b) as 2 * n_links ints. */
+int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links);
+
+/* Enqueue n_steps model steps of size dt. Does not wait for them. */
+int yb_sim_step(yb_sim* sim, float dt, int n_steps);
+/* Same, bracketed by CUDA events on the launching stream; waits, and returns
+ * the device time in milliseconds and the sum over steps of the cell count
+ * at the start of each step (the numerator of cell-updates/s). */
+int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
+    long long* cell_updates_out);
+/* Host-buffer round trip, timed on the host clock by the caller: copies the
+ * n cells at h_in to the device, takes n_steps steps, copies the state back
+ * to h_out and waits. */
+int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
+    int n_steps, float* h_out, int capacity, int* n_out);
+
+/* Current cell count (blocking read of d_n: Solution::get_d_n). */
+int yb_sim_n(yb_sim* sim, int* n_out);
+int yb_sim_sync(yb_sim* sim);
+
+/* ---- grid build ------------------------------------------------------------
+ * Grid::build (solvers.cuh:380-425) on n points of `lanes` floats each
+ * (3, 4, 5 or 7) resident at d_X. Writes the four public arrays:
+ * d_cube_id[n] sorted cube ids, d_point_id[n] original index per sorted slot,
+ * d_cube_start / d_cube_end [grid_size^3], inclusive, -1 / -2 when empty.
+ * Blocks until done. */
+int yb_grid_build(const float* d_X, int lanes, int n, int grid_size,
+    float cube_size, int* d_cube_id, int* d_point_id, int* d_cube_start,
+    int* d_cube_end);
+/* The 27 neighbour-cube offsets (d_nhood, solvers.cuh:428, :472-484) for a
+ * grid size, in the order user kernels index them. */
+int yb_nhood(int grid_size, int* h_nhood27);
+
+/* ---- link forces -------------------------------------------------------------
+ * link_forces<Pt> (links.cuh:128-133) with linear_force on n cells of
+ * `lanes` floats: adds -/+ strength * r / |r| to d_dX for every link (a, b)
+ * with a != b. d_links holds 2 * n_links ints. Blocks until done. */
+int yb_link_forces(const float* d_X, float* d_dX, int lanes, int n,
+    const int* d_links, int n_links, float strength);
+
+/* ---- polarity forces, evaluated once on the device ----------------------------
+ * bending_force (polarity.cuh:74-94) and bidirectional_polarization_force
+ * (:65-69) for n_pairs independent (Xi, Xj) pairs of Po_cell (5 floats each):
+ * out[k] = f(Xi[k], r = Xi[k] - Xj[k], |r|)  resp.  f(Xi[k], pol(Xj[k])). */
+int yb_bending_force(const float* h_Xi, const float* h_Xj, int n_pairs,
+    float* h_out);
+int yb_polarization_force(const float* h_Xi, const float* h_Xj, int n_pairs,
+    float* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YALLA_B200_H */

@@ -1,0 +1,281 @@
+"""Python host side of the ya||a B200 hot path.
+
+The product is the CUDA C++ header set in ``include/`` plus the compiled C ABI
+``include/yalla_b200.h``. This package is the thin ctypes binding above that
+ABI which the test-suite and ``bench.py`` use. The same binding drives three
+interchangeable libraries (see ``yalla_b200.h``):
+
+* ``product()``   -- ``yalla_b200/_lib/libyalla_b200.so`` (this repo's kernels)
+* ``reference()`` -- ``oracle/_ref/libyalla_ref.so`` (unmodified reference
+  headers compiled for sm_100a; the baseline arm and the A/B parity vote)
+* the CPU oracle is loaded by ``tests/`` and ``bench.py`` only, via
+  ``yalla_b200.load(path)``; nothing in this package imports ``oracle/``.
+
+There is no CPU fallback: ``product()`` raises if the CUDA library is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_LIB = os.path.join(_ROOT, "yalla_b200", "_lib", "libyalla_b200.so")
+REFERENCE_LIB = os.path.join(_ROOT, "oracle", "_ref", "libyalla_ref.so")
+
+YB_OK, YB_EINVAL, YB_ECUDA, YB_ENOSYS = 0, -1, -2, -3
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); mirrors include/yalla_b200.h one to one
+SIGNATURES = {
+    "yb_build_info": (ctypes.c_char_p, []),
+    "yb_last_error": (ctypes.c_char_p, []),
+    "yb_sim_create": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_float,
+                                     ctypes.POINTER(ctypes.c_void_p)]),
+    "yb_sim_destroy": (None, [ctypes.c_void_p]),
+    "yb_sim_lanes": (ctypes.c_int, [ctypes.c_void_p]),
+    "yb_sim_n_max": (ctypes.c_int, [ctypes.c_void_p]),
+    "yb_sim_set_param": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
+                                        ctypes.c_double]),
+    "yb_sim_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_int]),
+    "yb_sim_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, _c_int_p]),
+    "yb_sim_get_velocities": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int]),
+    "yb_sim_set_ints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
+                                       ctypes.c_void_p, ctypes.c_int]),
+    "yb_sim_get_ints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
+                                       ctypes.c_void_p, ctypes.c_int]),
+    "yb_sim_set_links": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int]),
+    "yb_sim_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
+                                   ctypes.c_int]),
+    "yb_sim_step_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
+                                         ctypes.c_int, _c_float_p,
+                                         ctypes.POINTER(ctypes.c_longlong)]),
+    "yb_sim_step_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_float,
+                                        ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_int, _c_int_p]),
+    "yb_sim_n": (ctypes.c_int, [ctypes.c_void_p, _c_int_p]),
+    "yb_sim_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "yb_grid_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_float,
+                                     ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_nhood": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "yb_link_forces": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_float]),
+    "yb_bending_force": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_void_p]),
+    "yb_polarization_force": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_void_p]),
+}
+
+MODEL_LANES = {
+    "springs": 3, "spring_tile": 3, "spring_grid": 3, "relu_tile": 3,
+    "relu_grid": 3, "protrusions": 3, "epithelium": 5, "growth": 5,
+    "branching": 7,
+}
+
+
+class YallaError(RuntimeError):
+    pass
+
+
+def _f32(array):
+    return np.ascontiguousarray(array, dtype=np.float32)
+
+
+def _i32(array):
+    return np.ascontiguousarray(array, dtype=np.int32)
+
+
+class Library:
+    """One loaded implementation of the C ABI."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise YallaError(
+                f"{path} is missing -- build it first "
+                "(python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(self.cdll, name)  # AttributeError if not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+
+    @property
+    def build_info(self):
+        return self.cdll.yb_build_info().decode()
+
+    def check(self, status, what):
+        if status != YB_OK:
+            raise YallaError(
+                f"{what} failed ({status}): "
+                f"{self.cdll.yb_last_error().decode()} [{self.build_info}]")
+
+    def sim(self, model, n_max, grid_size=50, cube_size=1.0):
+        return Sim(self, model, n_max, grid_size, cube_size)
+
+    # ---- stateless entry points -------------------------------------------
+    def nhood(self, grid_size):
+        out = np.zeros(27, dtype=np.int32)
+        self.check(self.cdll.yb_nhood(grid_size, out.ctypes.data), "yb_nhood")
+        return out
+
+    def grid_build(self, d_X, n, lanes, grid_size, cube_size, d_cube_id,
+                   d_point_id, d_cube_start, d_cube_end):
+        """All array arguments are device pointers (ints)."""
+        self.check(self.cdll.yb_grid_build(
+            d_X, lanes, n, grid_size, cube_size, d_cube_id, d_point_id,
+            d_cube_start, d_cube_end), "yb_grid_build")
+
+    def link_forces(self, d_X, d_dX, lanes, n, d_links, n_links, strength):
+        self.check(self.cdll.yb_link_forces(
+            d_X, d_dX, lanes, n, d_links, n_links, strength), "yb_link_forces")
+
+    def bending_force(self, Xi, Xj):
+        Xi, Xj = _f32(Xi), _f32(Xj)
+        out = np.zeros_like(Xi)
+        self.check(self.cdll.yb_bending_force(
+            Xi.ctypes.data, Xj.ctypes.data, len(Xi), out.ctypes.data),
+            "yb_bending_force")
+        return out
+
+    def polarization_force(self, Xi, Xj):
+        Xi, Xj = _f32(Xi), _f32(Xj)
+        out = np.zeros_like(Xi)
+        self.check(self.cdll.yb_polarization_force(
+            Xi.ctypes.data, Xj.ctypes.data, len(Xi), out.ctypes.data),
+            "yb_polarization_force")
+        return out
+
+
+class Sim:
+    """A named model: Solution<Pt, Solver> plus its user code, behind the ABI."""
+
+    def __init__(self, lib, model, n_max, grid_size=50, cube_size=1.0):
+        self.lib = lib
+        self.model = model
+        handle = ctypes.c_void_p()
+        lib.check(lib.cdll.yb_sim_create(
+            model.encode(), n_max, grid_size, cube_size, ctypes.byref(handle)),
+            f"yb_sim_create({model})")
+        self.handle = handle
+        self.lanes = lib.cdll.yb_sim_lanes(handle)
+        self.n_max = lib.cdll.yb_sim_n_max(handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.cdll.yb_sim_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_param(self, name, value):
+        self.lib.check(self.lib.cdll.yb_sim_set_param(
+            self.handle, name.encode(), float(value)), f"set_param({name})")
+
+    def set_state(self, X, reset_v=True):
+        X = _f32(X).reshape(-1, self.lanes)
+        self.lib.check(self.lib.cdll.yb_sim_set_state(
+            self.handle, X.ctypes.data, len(X), int(reset_v)), "set_state")
+
+    def get_state(self):
+        out = np.zeros((self.n_max, self.lanes), dtype=np.float32)
+        n = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_sim_get_state(
+            self.handle, out.ctypes.data, self.n_max, ctypes.byref(n)),
+            "get_state")
+        return out[:n.value].copy()
+
+    def get_velocities(self):
+        out = np.zeros((self.n_max, 3), dtype=np.float32)
+        self.lib.check(self.lib.cdll.yb_sim_get_velocities(
+            self.handle, out.ctypes.data, self.n_max), "get_velocities")
+        return out[:self.n()].copy()
+
+    def set_ints(self, name, values):
+        values = _i32(values)
+        self.lib.check(self.lib.cdll.yb_sim_set_ints(
+            self.handle, name.encode(), values.ctypes.data, len(values)),
+            f"set_ints({name})")
+
+    def get_ints(self, name):
+        out = np.zeros(self.n_max, dtype=np.int32)
+        self.lib.check(self.lib.cdll.yb_sim_get_ints(
+            self.handle, name.encode(), out.ctypes.data, self.n_max),
+            f"get_ints({name})")
+        return out[:self.n()].copy()
+
+    def set_links(self, links):
+        links = _i32(links).reshape(-1, 2)
+        self.lib.check(self.lib.cdll.yb_sim_set_links(
+            self.handle, links.ctypes.data, len(links)), "set_links")
+
+    def step(self, dt, n_steps=1):
+        self.lib.check(self.lib.cdll.yb_sim_step(self.handle, dt, n_steps),
+                       "step")
+
+    def step_timed(self, dt, n_steps):
+        """-> (milliseconds on the device, cell updates done)"""
+        ms = ctypes.c_float()
+        updates = ctypes.c_longlong()
+        self.lib.check(self.lib.cdll.yb_sim_step_timed(
+            self.handle, dt, n_steps, ctypes.byref(ms), ctypes.byref(updates)),
+            "step_timed")
+        return ms.value, updates.value
+
+    def step_host(self, X_in, dt, n_steps, X_out):
+        """Host buffers in, host buffers out; X_out must hold n_max cells."""
+        n = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_sim_step_host(
+            self.handle, X_in.ctypes.data, len(X_in), dt, n_steps,
+            X_out.ctypes.data, len(X_out), ctypes.byref(n)), "step_host")
+        return n.value
+
+    def n(self):
+        n = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_sim_n(self.handle, ctypes.byref(n)), "n")
+        return n.value
+
+    def sync(self):
+        self.lib.check(self.lib.cdll.yb_sim_sync(self.handle), "sync")
+
+
+def load(path):
+    return Library(path)
+
+
+_cache = {}
+
+
+def product():
+    """This repo's CUDA build. No fallback: fails loudly if it is missing."""
+    if "product" not in _cache:
+        _cache["product"] = Library(PRODUCT_LIB)
+    return _cache["product"]
+
+
+def reference():
+    """The unmodified reference headers compiled for sm_100a (baseline arm)."""
+    if "reference" not in _cache:
+        _cache["reference"] = Library(REFERENCE_LIB)
+    return _cache["reference"]

@@ -1,0 +1,666 @@
+// Implementation of the C ABI declared in include/yalla_b200.h on top of the
+// PUBLIC ya||a API only (Solution, take_step, Grid, Links, Property, ...).
+//
+// Built twice from this one source:
+//   -I include                       -> yalla_b200/_lib/libyalla_b200.so
+//   -I /root/reference/include       -> oracle/_ref/libyalla_ref.so
+// The few places that use extensions of this repo's headers are guarded by
+// #ifdef YALLA_B200 (defined by include/solvers.cuh).
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "models.cuh"
+
+#include "yalla_b200.h"
+
+namespace {
+
+thread_local std::string last_error;
+
+int fail(int code, const std::string& what)
+{
+    last_error = what;
+    return code;
+}
+
+int check_cuda(const char* where)
+{
+    const cudaError_t status = cudaGetLastError();
+    if (status == cudaSuccess) return YB_OK;
+    return fail(YB_ECUDA, std::string(where) + ": " + cudaGetErrorString(status));
+}
+
+}  // namespace
+
+
+// The interface every model implements.
+struct yb_sim {
+    virtual ~yb_sim() {}
+    virtual int lanes() const = 0;
+    virtual int n_max() const = 0;
+    virtual int set_param(const std::string& name, double value)
+    {
+        return fail(YB_EINVAL, "unknown parameter " + name);
+    }
+    virtual int set_state(const float* h_X, int n, int reset_v) = 0;
+    virtual int get_state(float* h_X, int capacity, int* n_out) = 0;
+    virtual int get_velocities(float* h_v, int capacity) = 0;
+    virtual int set_ints(const std::string& name, const int* values, int n)
+    {
+        return fail(YB_EINVAL, "model has no int property " + name);
+    }
+    virtual int get_ints(const std::string& name, int* values, int capacity)
+    {
+        return fail(YB_EINVAL, "model has no int property " + name);
+    }
+    virtual int set_links(const int* h_links, int n_links)
+    {
+        return fail(YB_EINVAL, "model has no links");
+    }
+    // One model step; returns the cell count at the start of the step if the
+    // model tracks it on the host (growing models), else -1.
+    virtual int step(float dt) = 0;
+    virtual int current_n() = 0;
+};
+
+namespace {
+
+// State handling shared by all models: a Solution plus host-side glue.
+template<typename Pt, template<typename> class Solver>
+struct Sim_base : yb_sim {
+    Solution<Pt, Solver> cells;
+    int n_host;  // cell count as last set/read by the host
+
+    template<typename... Args>
+    Sim_base(int n_max, Args... args) : cells{n_max, args...}, n_host{0}
+    {
+        memset(cells.h_X, 0, sizeof(Pt) * static_cast<size_t>(n_max));
+        *cells.h_n = 0;
+        cells.copy_to_device();
+    }
+    int lanes() const override { return sizeof(Pt) / sizeof(float); }
+    int n_max() const override { return cells.n_max; }
+
+    int set_state(const float* h_X, int n, int reset_v) override
+    {
+        if (n < 0 || n > cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        memcpy(cells.h_X, h_X, sizeof(Pt) * static_cast<size_t>(n));
+        *cells.h_n = n;
+        cells.copy_to_device();
+        if (reset_v)
+            cudaMemset(cells.d_old_v, 0,
+                sizeof(float3) * static_cast<size_t>(cells.n_max));
+        n_host = n;
+        return check_cuda("set_state");
+    }
+    int get_state(float* h_X, int capacity, int* n_out) override
+    {
+        cells.copy_to_host();
+        const int n = *cells.h_n;
+        if (n > capacity) return fail(YB_EINVAL, "capacity < n");
+        memcpy(h_X, cells.h_X, sizeof(Pt) * static_cast<size_t>(n));
+        if (n_out) *n_out = n;
+        n_host = n;
+        return check_cuda("get_state");
+    }
+    int get_velocities(float* h_v, int capacity) override
+    {
+        const int n = cells.get_d_n();
+        if (n > capacity) return fail(YB_EINVAL, "capacity < n");
+        cudaMemcpy(h_v, cells.d_old_v, sizeof(float3) * static_cast<size_t>(n),
+            cudaMemcpyDeviceToHost);
+        return check_cuda("get_velocities");
+    }
+    int current_n() override { return n_host = cells.get_d_n(); }
+
+    int set_fix(const std::string& name, double value)
+    {
+        if (name == "fix_point") {
+            cells.set_fixed(static_cast<int>(value));
+            return YB_OK;
+        }
+        if (name == "fix_point_xy") {
+            cells.set_fixed_xy(static_cast<int>(value));
+            return YB_OK;
+        }
+        if (name == "fix_com") {
+            cells.set_fixed();
+            return YB_OK;
+        }
+        return 1;  // not a fixing parameter
+    }
+};
+
+int set_spring_length(double value)
+{
+    const float length = static_cast<float>(value);
+    cudaMemcpyToSymbol(models::d_spring_length, &length, sizeof(float));
+    return check_cuda("spring_length");
+}
+
+// ---- float3 models with a stateless functor --------------------------------
+template<template<typename> class Solver, Pairwise_interaction<float3> force>
+struct Spring_sim : Sim_base<float3, Solver> {
+    using Base = Sim_base<float3, Solver>;
+    template<typename... Args>
+    Spring_sim(int n_max, Args... args) : Base{n_max, args...}
+    {
+        set_spring_length(0.5);
+    }
+    int set_param(const std::string& name, double value) override
+    {
+        if (name == "spring_length") return set_spring_length(value);
+        const int fixed = Base::set_fix(name, value);
+        return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+    }
+    int step(float dt) override
+    {
+        this->cells.template take_step<force>(dt);
+        return -1;
+    }
+};
+
+// ---- float3 + Links: relu_force with link_forces as generic force -----------
+struct Protrusion_sim : Sim_base<float3, Grid_solver> {
+    using Base = Sim_base<float3, Grid_solver>;
+    Links links;
+    Protrusion_sim(int n_max, int grid_size, float cube_size)
+        : Base{n_max, grid_size, cube_size}, links{4 * n_max}
+    {
+        links.set_d_n(0);
+    }
+    int set_param(const std::string& name, double value) override
+    {
+        if (name == "link_strength") {
+            links.strength = static_cast<float>(value);
+            return YB_OK;
+        }
+        const int fixed = Base::set_fix(name, value);
+        return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+    }
+    int set_links(const int* h_links, int n_links) override
+    {
+        if (n_links > links.n_max) return fail(YB_EINVAL, "too many links");
+        memcpy(links.h_link, h_links, sizeof(Link) * static_cast<size_t>(n_links));
+        *links.h_n = n_links;
+        links.copy_to_device();
+        return check_cuda("set_links");
+    }
+    int step(float dt) override
+    {
+        auto pull = [this](const int n, const float3* __restrict__ d_X,
+                        float3* d_dX) { link_forces(links, d_X, d_dX); };
+        cells.take_step<relu_force<float3>>(dt, pull);
+        return -1;
+    }
+};
+
+// ---- Po_cell epithelium -------------------------------------------------------------
+struct Epithelium_sim : Sim_base<Po_cell, Grid_solver> {
+    using Base = Sim_base<Po_cell, Grid_solver>;
+    Epithelium_sim(int n_max, int grid_size, float cube_size)
+        : Base{n_max, grid_size, cube_size}
+    {}
+    int set_param(const std::string& name, double value) override
+    {
+        const int fixed = Base::set_fix(name, value);
+        return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+    }
+    int step(float dt) override
+    {
+        cells.take_step<models::layer_force, friction_on_background>(dt);
+        return -1;
+    }
+};
+
+// Models with a cell type and neighbour counters as Property arrays.
+template<typename Pt>
+struct Typed_sim : Sim_base<Pt, Grid_solver> {
+    using Base = Sim_base<Pt, Grid_solver>;
+    Property<models::Cell_types> type;
+    Property<int> n_mes_nbs, n_epi_nbs;
+
+    Typed_sim(int n_max, int grid_size, float cube_size)
+        : Base{n_max, grid_size, cube_size}, type{n_max},
+          n_mes_nbs{n_max, "n_mes_nbs"}, n_epi_nbs{n_max, "n_epi_nbs"}
+    {
+        for (int i = 0; i < n_max; i++) {
+            type.h_prop[i] = models::mesenchyme;
+            n_mes_nbs.h_prop[i] = 0;
+            n_epi_nbs.h_prop[i] = 0;
+        }
+        type.copy_to_device();
+        n_mes_nbs.copy_to_device();
+        n_epi_nbs.copy_to_device();
+        bind();
+    }
+    // The functors find the property arrays through __device__ pointers.
+    void bind()
+    {
+        cudaMemcpyToSymbol(models::d_type, &type.d_prop, sizeof(type.d_prop));
+        cudaMemcpyToSymbol(
+            models::d_mes_nbs, &n_mes_nbs.d_prop, sizeof(n_mes_nbs.d_prop));
+        cudaMemcpyToSymbol(
+            models::d_epi_nbs, &n_epi_nbs.d_prop, sizeof(n_epi_nbs.d_prop));
+    }
+    int set_ints(const std::string& name, const int* values, int n) override
+    {
+        if (n > this->cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        if (name == "type") {
+            for (int i = 0; i < n; i++)
+                type.h_prop[i] = static_cast<models::Cell_types>(values[i]);
+            type.copy_to_device();
+            return check_cuda("set type");
+        }
+        return yb_sim::set_ints(name, values, n);
+    }
+    int get_ints(const std::string& name, int* values, int capacity) override
+    {
+        const int n = this->cells.get_d_n();
+        if (n > capacity) return fail(YB_EINVAL, "capacity < n");
+        if (name == "type") {
+            type.copy_to_host();
+            for (int i = 0; i < n; i++) values[i] = type.h_prop[i];
+        } else if (name == "mes_nbs") {
+            n_mes_nbs.copy_to_host();
+            memcpy(values, n_mes_nbs.h_prop, sizeof(int) * size_t(n));
+        } else if (name == "epi_nbs") {
+            n_epi_nbs.copy_to_host();
+            memcpy(values, n_epi_nbs.h_prop, sizeof(int) * size_t(n));
+        } else {
+            return yb_sim::get_ints(name, values, capacity);
+        }
+        return check_cuda("get_ints");
+    }
+    // reset_nbs of passive_growth.cu:107-113 / branching.cu:188-193, using the
+    // n handed to the callback instead of reading d_n back.
+    void reset_counters(int n)
+    {
+        cudaMemsetAsync(n_mes_nbs.d_prop, 0, sizeof(int) * size_t(n));
+        cudaMemsetAsync(n_epi_nbs.d_prop, 0, sizeof(int) * size_t(n));
+    }
+};
+
+// ---- Po_cell growth ------------------------------------------------------------------
+struct Growth_sim : Typed_sim<Po_cell> {
+    curandState* d_state = nullptr;
+    float prolif_rate = 0.006f, mean_dist = 0.75f;
+    int seed = 2;
+    bool seeded = false;
+
+    Growth_sim(int n_max, int grid_size, float cube_size)
+        : Typed_sim<Po_cell>{n_max, grid_size, cube_size}
+    {
+        cudaMalloc(&d_state, sizeof(curandState) * size_t(n_max));
+    }
+    ~Growth_sim() override { cudaFree(d_state); }
+    int set_param(const std::string& name, double value) override
+    {
+        if (name == "prolif_rate") {
+            prolif_rate = static_cast<float>(value);
+        } else if (name == "mean_dist") {
+            mean_dist = static_cast<float>(value);
+        } else if (name == "seed") {
+            seed = static_cast<int>(value);
+            seeded = false;
+        } else {
+            const int fixed = Base::set_fix(name, value);
+            return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+        }
+        return YB_OK;
+    }
+    int step(float dt) override
+    {
+        const int n_max = cells.n_max;
+        if (!seeded) {
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128>>>(
+                n_max, seed, d_state);
+            seeded = true;
+        }
+        bind();
+        auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
+                             Po_cell* d_dX) { reset_counters(n); };
+        const int n = cells.get_d_n();
+        cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
+        if (prolif_rate > 0 && n > 0)
+            models::proliferate<<<(n + 128 - 1) / 128, 128>>>(prolif_rate,
+                mean_dist, n, n_max, d_state, cells.d_X, cells.d_old_v,
+                cells.d_n);
+        return n;
+    }
+};
+
+// ---- 7-float branching cell --------------------------------------------------------
+struct Branching_sim : Typed_sim<models::Cell> {
+    Branching_sim(int n_max, int grid_size, float cube_size)
+        : Typed_sim<models::Cell>{n_max, grid_size, cube_size}
+    {}
+    int set_param(const std::string& name, double value) override
+    {
+        const int fixed = Base::set_fix(name, value);
+        return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+    }
+    int step(float dt) override
+    {
+        bind();
+        auto reset_nbs = [this](const int n, const models::Cell* __restrict__ d_X,
+                             models::Cell* d_dX) { reset_counters(n); };
+        cells.take_step<models::epi_turing_mes_noturing>(dt, reset_nbs);
+        return -1;
+    }
+};
+
+}  // namespace
+
+
+namespace {
+using Lanes4 = Lanes4_cell;
+
+template<typename Pt>
+int grid_build(const float* d_X, int n, int grid_size, float cube_size,
+    int* d_cube_id, int* d_point_id, int* d_cube_start, int* d_cube_end)
+{
+    Grid grid{n, grid_size};
+    grid.build(n, reinterpret_cast<const Pt*>(d_X), cube_size);
+    const size_t cells = sizeof(int) * static_cast<size_t>(n);
+    const size_t cubes = sizeof(int) * static_cast<size_t>(grid.n_cubes);
+    cudaMemcpy(d_cube_id, grid.d_cube_id, cells, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(d_point_id, grid.d_point_id, cells, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(d_cube_start, grid.d_cube_start, cubes, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(d_cube_end, grid.d_cube_end, cubes, cudaMemcpyDeviceToDevice);
+    cudaDeviceSynchronize();
+    return check_cuda("yb_grid_build");
+}
+}  // namespace
+
+namespace {
+template<typename Pt>
+int run_link_forces(const float* d_X, float* d_dX, int n, const int* d_links,
+    int n_links, float strength)
+{
+    Links links{n_links, strength};
+    cudaMemcpy(links.d_link, d_links, sizeof(Link) * static_cast<size_t>(n_links),
+        cudaMemcpyDeviceToDevice);
+    links.set_d_n(n_links);
+#ifdef YALLA_B200
+    // Outside a solver step nobody tells link_forces how many cells there are;
+    // provide the context the solver would.
+    yb::Stage_context context{n, n, 0};
+    yb::current_stage() = &context;
+#endif
+    link_forces(links, reinterpret_cast<const Pt*>(d_X),
+        reinterpret_cast<Pt*>(d_dX));
+#ifdef YALLA_B200
+    yb::current_stage() = nullptr;
+#endif
+    cudaDeviceSynchronize();
+    return check_cuda("yb_link_forces");
+}
+}  // namespace
+
+namespace {
+__global__ void bending_pairs(
+    const Po_cell* Xi, const Po_cell* Xj, int n_pairs, Po_cell* out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const Po_cell r = Xi[k] - Xj[k];
+    const float dist = norm3df(r.x, r.y, r.z);
+    out[k] = bending_force(Xi[k], r, dist);
+}
+
+__global__ void polarization_pairs(
+    const Po_cell* Xi, const Po_cell* Xj, int n_pairs, Po_cell* out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const Polarity p{Xj[k].theta, Xj[k].phi};
+    out[k] = bidirectional_polarization_force(Xi[k], p);
+}
+
+template<typename Kernel>
+int run_pairs(Kernel kernel, const float* h_Xi, const float* h_Xj, int n_pairs,
+    float* h_out)
+{
+    if (n_pairs <= 0) return fail(YB_EINVAL, "bad size");
+    const size_t bytes = sizeof(Po_cell) * static_cast<size_t>(n_pairs);
+    Po_cell *d_Xi, *d_Xj, *d_out;
+    cudaMalloc(&d_Xi, bytes);
+    cudaMalloc(&d_Xj, bytes);
+    cudaMalloc(&d_out, bytes);
+    cudaMemcpy(d_Xi, h_Xi, bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_Xj, h_Xj, bytes, cudaMemcpyHostToDevice);
+    kernel<<<(n_pairs + 127) / 128, 128>>>(d_Xi, d_Xj, n_pairs, d_out);
+    cudaMemcpy(h_out, d_out, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_Xi);
+    cudaFree(d_Xj);
+    cudaFree(d_out);
+    return check_cuda("polarity pairs");
+}
+}  // namespace
+
+
+extern "C" {
+
+const char* yb_build_info(void)
+{
+#ifdef YALLA_B200
+    return "yalla-b200 (B200-native headers, sm_100a)";
+#else
+    return "yalla-reference (unmodified reference headers, sm_100a)";
+#endif
+}
+
+const char* yb_last_error(void) { return last_error.c_str(); }
+
+int yb_sim_create(const char* model, int n_max, int grid_size, float cube_size,
+    yb_sim** out)
+{
+    if (!model || !out || n_max <= 0) return fail(YB_EINVAL, "bad argument");
+    const std::string name = model;
+    if (grid_size <= 0) grid_size = 50;
+    if (!(cube_size > 0)) cube_size = 1.f;
+    yb_sim* sim = nullptr;
+    if (name == "springs")
+        sim = new Spring_sim<Tile_solver, models::spring>(n_max);
+    else if (name == "spring_tile")
+        sim = new Spring_sim<Tile_solver, models::clipped_spring>(n_max);
+    else if (name == "spring_grid")
+        sim = new Spring_sim<Grid_solver, models::clipped_spring>(
+            n_max, grid_size, cube_size);
+    else if (name == "relu_tile")
+        sim = new Spring_sim<Tile_solver, relu_force<float3>>(n_max);
+    else if (name == "relu_grid")
+        sim = new Spring_sim<Grid_solver, relu_force<float3>>(
+            n_max, grid_size, cube_size);
+    else if (name == "protrusions")
+        sim = new Protrusion_sim(n_max, grid_size, cube_size);
+    else if (name == "epithelium")
+        sim = new Epithelium_sim(n_max, grid_size, cube_size);
+    else if (name == "growth")
+        sim = new Growth_sim(n_max, grid_size, cube_size);
+    else if (name == "branching")
+        sim = new Branching_sim(n_max, grid_size, cube_size);
+    else
+        return fail(YB_EINVAL, "unknown model " + name);
+    const int status = check_cuda("yb_sim_create");
+    if (status != YB_OK) {
+        delete sim;
+        return status;
+    }
+    *out = sim;
+    return YB_OK;
+}
+
+void yb_sim_destroy(yb_sim* sim)
+{
+    cudaDeviceSynchronize();
+    delete sim;
+}
+
+int yb_sim_lanes(const yb_sim* sim) { return sim->lanes(); }
+int yb_sim_n_max(const yb_sim* sim) { return sim->n_max(); }
+
+int yb_sim_set_param(yb_sim* sim, const char* name, double value)
+{
+    return sim->set_param(name, value);
+}
+
+int yb_sim_set_state(yb_sim* sim, const float* h_X, int n, int reset_v)
+{
+    return sim->set_state(h_X, n, reset_v);
+}
+
+int yb_sim_get_state(yb_sim* sim, float* h_X, int capacity, int* n_out)
+{
+    return sim->get_state(h_X, capacity, n_out);
+}
+
+int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity)
+{
+    return sim->get_velocities(h_v, capacity);
+}
+
+int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n)
+{
+    return sim->set_ints(name, h_values, n);
+}
+
+int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity)
+{
+    return sim->get_ints(name, h_values, capacity);
+}
+
+int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links)
+{
+    return sim->set_links(h_links, n_links);
+}
+
+int yb_sim_step(yb_sim* sim, float dt, int n_steps)
+{
+    for (int k = 0; k < n_steps; k++) sim->step(dt);
+    return check_cuda("yb_sim_step");
+}
+
+int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
+    long long* cell_updates_out)
+{
+    cudaEvent_t start, stop;
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+    long long updates = 0;
+    const int n_start = sim->current_n();
+    cudaDeviceSynchronize();
+    cudaEventRecord(start, 0);
+    for (int k = 0; k < n_steps; k++) {
+        const int n = sim->step(dt);
+        updates += n >= 0 ? n : n_start;
+    }
+    cudaEventRecord(stop, 0);
+    cudaEventSynchronize(stop);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, start, stop);
+    cudaEventDestroy(start);
+    cudaEventDestroy(stop);
+    if (ms_out) *ms_out = ms;
+    if (cell_updates_out) *cell_updates_out = updates;
+    return check_cuda("yb_sim_step_timed");
+}
+
+int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
+    int n_steps, float* h_out, int capacity, int* n_out)
+{
+    int status = sim->set_state(h_in, n, 0);
+    if (status != YB_OK) return status;
+    for (int k = 0; k < n_steps; k++) sim->step(dt);
+    return sim->get_state(h_out, capacity, n_out);
+}
+
+int yb_sim_n(yb_sim* sim, int* n_out)
+{
+    *n_out = sim->current_n();
+    return check_cuda("yb_sim_n");
+}
+
+int yb_sim_sync(yb_sim* sim)
+{
+    cudaDeviceSynchronize();
+    return check_cuda("yb_sim_sync");
+}
+
+
+// ---- grid build ---------------------------------------------------------------
+
+int yb_grid_build(const float* d_X, int lanes, int n, int grid_size,
+    float cube_size, int* d_cube_id, int* d_point_id, int* d_cube_start,
+    int* d_cube_end)
+{
+    if (n <= 0 || grid_size <= 0) return fail(YB_EINVAL, "bad size");
+    switch (lanes) {
+        case 3:
+            return grid_build<float3>(d_X, n, grid_size, cube_size, d_cube_id,
+                d_point_id, d_cube_start, d_cube_end);
+        case 4:
+            return grid_build<Lanes4>(d_X, n, grid_size, cube_size, d_cube_id,
+                d_point_id, d_cube_start, d_cube_end);
+        case 5:
+            return grid_build<Po_cell>(d_X, n, grid_size, cube_size, d_cube_id,
+                d_point_id, d_cube_start, d_cube_end);
+        case 7:
+            return grid_build<models::Cell>(d_X, n, grid_size, cube_size,
+                d_cube_id, d_point_id, d_cube_start, d_cube_end);
+    }
+    return fail(YB_EINVAL, "lanes must be 3, 4, 5 or 7");
+}
+
+int yb_nhood(int grid_size, int* h_nhood27)
+{
+    // The table is written by the grid solver's constructor.
+    Solution<float3, Grid_solver> probe{1, grid_size};
+    cudaMemcpyFromSymbol(h_nhood27, d_nhood, 27 * sizeof(int));
+    return check_cuda("yb_nhood");
+}
+
+
+// ---- link forces --------------------------------------------------------------
+
+int yb_link_forces(const float* d_X, float* d_dX, int lanes, int n,
+    const int* d_links, int n_links, float strength)
+{
+    if (n <= 0 || n_links <= 0) return fail(YB_EINVAL, "bad size");
+    switch (lanes) {
+        case 3:
+            return run_link_forces<float3>(
+                d_X, d_dX, n, d_links, n_links, strength);
+        case 4:
+            return run_link_forces<Lanes4>(
+                d_X, d_dX, n, d_links, n_links, strength);
+        case 5:
+            return run_link_forces<Po_cell>(
+                d_X, d_dX, n, d_links, n_links, strength);
+        case 7:
+            return run_link_forces<models::Cell>(
+                d_X, d_dX, n, d_links, n_links, strength);
+    }
+    return fail(YB_EINVAL, "lanes must be 3, 4, 5 or 7");
+}
+
+
+// ---- polarity forces -------------------------------------------------------------
+
+int yb_bending_force(
+    const float* h_Xi, const float* h_Xj, int n_pairs, float* h_out)
+{
+    return run_pairs(bending_pairs, h_Xi, h_Xj, n_pairs, h_out);
+}
+
+int yb_polarization_force(
+    const float* h_Xi, const float* h_Xj, int n_pairs, float* h_out)
+{
+    return run_pairs(polarization_pairs, h_Xi, h_Xj, n_pairs, h_out);
+}
+
+}  // extern "C"
