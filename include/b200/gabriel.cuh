@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(GABRIEL_THREADS) sweep_gabriel(
 
             // 1. every cell within cube_size, in the reference's sweep order
             for (int r = 0; r < SWEEP_ROWS; r++) {
-                const long long c = my_cube + (long long)row_shift(r, grid_size);
+                const int c = my_cube + row_shift(r, grid_size);
                 const int lo = __ldg(offset + clamp_cube(c - 1, n_cubes));
                 const int hi = __ldg(offset + clamp_cube(c + 2, n_cubes));
                 for (int q = lo; q < hi; q++) {

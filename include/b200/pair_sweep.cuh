@@ -50,11 +50,12 @@
 namespace yb {
 
 constexpr int SWEEP_THREADS = 128;
-constexpr int SWEEP_STAGE_CAP = 2048;  // staged pos4 records per round (<= 4096)
+constexpr int SWEEP_STAGE_CAP = 1536;  // staged pos4 records per round (<= 4095)
 constexpr int SWEEP_LIST_CAP = 32;     // neighbour-list entries per batch
 constexpr int SWEEP_ROWS = 9;
 constexpr size_t SWEEP_SMEM =
     size_t(SWEEP_STAGE_CAP) * sizeof(float4) +
+    size_t(SWEEP_ROWS) * SWEEP_THREADS * sizeof(uint32_t) +
     size_t(SWEEP_LIST_CAP) * SWEEP_THREADS * sizeof(uint16_t);
 // Squared-distance pre-filter: keep everything the exact test could accept.
 // The rounding error of dx*dx+dy*dy+dz*dz is a few 1e-7 relative; 1e-5 is
@@ -122,9 +123,11 @@ __device__ __forceinline__ int row_shift(int r, int grid_size)
     return dy * grid_size + dz * grid_size * grid_size;
 }
 
-__device__ __forceinline__ int clamp_cube(long long c, int n_cubes)
+// Cube ids stay far below 2^30 (grid_size <= 1024), so id +- one z-layer fits
+// an int.
+__device__ __forceinline__ int clamp_cube(int c, int n_cubes)
 {
-    return static_cast<int>(c < 0 ? 0 : (c > n_cubes ? n_cubes : c));
+    return c < 0 ? 0 : (c > n_cubes ? n_cubes : c);
 }
 
 template<typename Pt>
@@ -258,7 +261,7 @@ __device__ __forceinline__ void finish_drift(float3 my_partial,
 // otherwise d_dX is write-only (no zero fill anywhere).
 template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
     float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
+__global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
     const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
@@ -268,7 +271,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
     using L = Layout<Pt>;
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     float4* s_pos = reinterpret_cast<float4*>(sweep_smem);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_pos + SWEEP_STAGE_CAP);
+    uint32_t* s_range = reinterpret_cast<uint32_t*>(s_pos + SWEEP_STAGE_CAP);
+    uint16_t* s_list =
+        reinterpret_cast<uint16_t*>(s_range + SWEEP_ROWS * SWEEP_THREADS);
     __shared__ int s_row_lo[SWEEP_ROWS];     // first global slot of row span
     __shared__ int s_row_v[SWEEP_ROWS + 1];  // start in the concatenated spans
     __shared__ float s_red[3][SWEEP_THREADS / 32];
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
 
         if (t < SWEEP_ROWS) {
             const int last_slot = min(first_slot + SWEEP_THREADS, n) - 1;
-            const long long shift = row_shift(t, grid_size);
+            const int shift = row_shift(t, grid_size);
             const int lo = __ldg(offset +
                 clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, n_cubes));
             const int hi = __ldg(offset +
@@ -304,6 +309,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
         if (live) {
             me = __ldg(pos4 + k);
             my_cube = __ldg(cube_sorted + k);
+        }
+        // This thread's candidate slots per row, as global slot numbers. The 18
+        // loads are independent and fly while the spans are being staged.
+        int my_lo[SWEEP_ROWS], my_hi[SWEEP_ROWS];
+#pragma unroll
+        for (int r = 0; r < SWEEP_ROWS; r++) {
+            const int c = my_cube + row_shift(r, grid_size);
+            my_lo[r] = live ? __ldg(offset + clamp_cube(c - 1, n_cubes)) : 0;
+            my_hi[r] = live ? __ldg(offset + clamp_cube(c + 2, n_cubes)) : 0;
         }
         __syncthreads();
         if (t == 0) {
@@ -341,49 +355,58 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
                             uint32_t(b - a) * sizeof(float4), &s_bar);
                 }
             }
+            // window-relative [a, b) per row, packed a | b << 16, parked in
+            // shared memory so the scan below can index rows dynamically
+#pragma unroll
+            for (int r = 0; r < SWEEP_ROWS; r++) {
+                const int base = s_row_v[r] - s_row_lo[r] - v0;
+                const int a = min(max(my_lo[r] + base, 0), SWEEP_STAGE_CAP);
+                const int b = min(max(my_hi[r] + base, a), SWEEP_STAGE_CAP);
+                s_range[r * SWEEP_THREADS + t] = uint32_t(a) | (uint32_t(b) << 16);
+            }
             mbar_wait(&s_bar, parity);
             parity ^= 1u;
 
-            // -- phase 1 + 2, in batches of at most LIST_CAP accepted candidates
-            int r = live ? 0 : SWEEP_ROWS;  // next row to open
-            int a = 0, b = 0;               // current window-relative sub-range
-            bool window_done = false;
-            while (!window_done) {
+            // -- phase 1 (scan) and phase 2 (interact). One pass unless a list
+            //    overflows; then the scan resumes where it stopped.
+            int r0 = 0, a0 = -1;
+            bool pending = live;
+            while (pending) {
                 int listed = 0;
-                while (listed < SWEEP_LIST_CAP) {
-                    if (a >= b) {
-                        if (r == SWEEP_ROWS) {
-                            window_done = true;
-                            break;
+                pending = false;
+                for (int r = r0; r < SWEEP_ROWS; r++) {
+                    const uint32_t range = s_range[r * SWEEP_THREADS + t];
+                    int a = (r == r0 && a0 >= 0) ? a0 : int(range & 0xffffu);
+                    const int b = int(range >> 16);
+                    const uint16_t tag = uint16_t(r << 12);
+                    for (; a < b; a++) {
+                        const float4 p = s_pos[a];
+                        const float dx = me.x - p.x, dy = me.y - p.y,
+                                    dz = me.z - p.z;
+                        const float d2 = dx * dx + dy * dy + dz * dz;
+                        if (!(d2 > reach2)) {
+                            if (listed == SWEEP_LIST_CAP) {
+                                pending = true;
+                                break;
+                            }
+                            s_list[listed * SWEEP_THREADS + t] = tag | uint16_t(a);
+                            listed++;
                         }
-                        const long long c = my_cube + (long long)row_shift(r, grid_size);
-                        const int lo = __ldg(offset + clamp_cube(c - 1, n_cubes));
-                        const int hi = __ldg(offset + clamp_cube(c + 2, n_cubes));
-                        // to window-relative indices, clipped to the window
-                        const int base = s_row_v[r] - s_row_lo[r] - v0;
-                        a = max(lo + base, 0);
-                        b = min(hi + base, SWEEP_STAGE_CAP);
-                        r++;
-                        // tag = row of this sub-range, for phase 2
-                        continue;
                     }
-                    const float4 p = s_pos[a];
-                    const float dx = me.x - p.x, dy = me.y - p.y, dz = me.z - p.z;
-                    const float d2 = dx * dx + dy * dy + dz * dz;
-                    if (!(d2 > reach2)) {
-                        s_list[listed * SWEEP_THREADS + t] =
-                            static_cast<uint16_t>(((r - 1) << 12) | a);
-                        listed++;
+                    if (pending) {
+                        r0 = r, a0 = a;
+                        break;
                     }
-                    a++;
                 }
 
                 for (int e = 0; e < listed; e++) {
                     const unsigned entry = s_list[e * SWEEP_THREADS + t];
                     const int row = entry >> 12, at = entry & 4095;
-                    const float4 pj = s_pos[at];
                     const int kj = s_row_lo[row] + (v0 + at - s_row_v[row]);
                     const float4* aux_j = aux + size_t(kj) * L::aux_vec4;
+                    // issued early so the L2 round trip overlaps the functor
+                    const float3 vj = velocity_of<Pt>(aux_j);
+                    const float4 pj = s_pos[at];
                     const Pt Xj = assemble_pt<Pt>(pj, aux_j);
                     const Pt rij = Xi - Xj;
                     const float dist = norm3df(rij.x, rij.y, rij.z);
@@ -393,8 +416,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) sweep_cubes(
                     F += pw_int(Xi, rij, dist, my_id, j_id);
                     const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
                     sum_friction += friction;
-                    if (friction != 0.f)
-                        sum_v += friction * velocity_of<Pt>(aux_j);
+                    if (friction != 0.f) sum_v += friction * vj;
                 }
             }
         }
