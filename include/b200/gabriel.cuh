@@ -170,11 +170,12 @@ protected:
     void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
         const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
-        bool binned_by_predictor)
+        bool binned_by_predictor, cudaEvent_t before_sweep = nullptr)
     {
         this->build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
         const int ctas = this->persistent_ctas(
             prepare<pw_int, pw_friction, SEEDED>(), yb::GABRIEL_THREADS, max_ctas);
+        if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
         yb::sweep_gabriel<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::GABRIEL_THREADS, 0, s>>>(d_n, this->n_max, this->pos4,
                 this->aux, this->cube_sorted, this->sort.offset, this->cube_size,

@@ -287,6 +287,32 @@ public:
     // default stream, like every launch in a ya||a model).
     cudaStream_t stream = 0;
 
+    // Extension: time the pairwise sweep kernels with CUDA events on the
+    // launching stream (bench.py's roofline needs the dominant kernel's own
+    // duration). While enabled, steps are issued directly instead of replayed
+    // from a graph. read_sweep_profile() waits for the stream and returns the
+    // accumulated milliseconds and number of sweep launches since the last read.
+    void profile_sweeps(bool enable)
+    {
+        read_sweep_profile(nullptr, nullptr);
+        profiling = enable;
+    }
+    void read_sweep_profile(float* total_ms, int* launches)
+    {
+        YB_CUDA(cudaStreamSynchronize(stream));
+        float sum = 0.f;
+        for (auto& pair : sweep_events) {
+            float ms = 0.f;
+            YB_CUDA(cudaEventElapsedTime(&ms, pair.first, pair.second));
+            sum += ms;
+            cudaEventDestroy(pair.first);
+            cudaEventDestroy(pair.second);
+        }
+        if (total_ms) *total_ms = sum;
+        if (launches) *launches = static_cast<int>(sweep_events.size());
+        sweep_events.clear();
+    }
+
 protected:
     Pt *d_X, *d_dX, *d_X1, *d_dX1;
     float3* d_old_v;
@@ -328,7 +354,7 @@ protected:
         }
 
         Generic_forces<Pt> none;
-        if (!yb::graphs_enabled()) {
+        if (!yb::graphs_enabled() || profiling) {
             enqueue_stage<pw_int, pw_friction, false>(
                 stream, 0, dt, mode0, 0, none);
             enqueue_stage<pw_int, pw_friction, false>(
@@ -370,6 +396,8 @@ private:
     int max_sweep_ctas;
     cudaStream_t capture_stream;
     std::vector<yb::Step_graph> graphs;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
 
     // One Heun stage: [seed dX with generic forces] -> pairwise sweep (writes
     // dX or dX1 and the stage's drift) -> predictor or corrector update.
@@ -390,9 +418,18 @@ private:
             yb::current_stage() = nullptr;
         }
         const bool binned_by_predictor = stage == 1;
+        cudaEvent_t sweep_start = nullptr, sweep_stop = nullptr;
+        if (profiling) {
+            YB_CUDA(cudaEventCreate(&sweep_start));
+            YB_CUDA(cudaEventCreate(&sweep_stop));
+        }
         Computer<Pt>::template pwints<pw_int, pw_friction, SEEDED>(s, d_n,
             X_stage, d_old_v, dX_stage, d_partials, max_sweep_ctas, stage,
-            drift_mode, fix_point, d_ctl, binned_by_predictor);
+            drift_mode, fix_point, d_ctl, binned_by_predictor, sweep_start);
+        if (profiling) {
+            YB_CUDA(cudaEventRecord(sweep_stop, s));
+            sweep_events.emplace_back(sweep_start, sweep_stop);
+        }
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0) {
             Computer<Pt>::predict(s, blocks, d_n, dt, d_X, d_dX, d_X1, d_ctl);
@@ -427,10 +464,11 @@ protected:
     void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
         const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
-        bool /*binned_by_predictor*/)
+        bool /*binned_by_predictor*/, cudaEvent_t before_sweep = nullptr)
     {
         int blocks = yb::ceil_div(n_max > 0 ? n_max : 1, yb::TILE_THREADS);
         if (blocks > max_ctas) blocks = max_ctas;
+        if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
         yb::sweep_tiles<Pt, pw_int, pw_friction, SEEDED>
             <<<blocks, yb::TILE_THREADS, 0, s>>>(d_n, n_max, d_X, d_old_v, d_dX,
                 d_partials, stage, drift_mode, fix_point, d_ctl);
@@ -678,11 +716,12 @@ protected:
     void pwints(cudaStream_t s, const int* d_n, const Pt* d_X,
         const float3* d_old_v, Pt* d_dX, float* d_partials, int max_ctas,
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
-        bool binned_by_predictor)
+        bool binned_by_predictor, cudaEvent_t before_sweep = nullptr)
     {
         build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
         const int ctas = persistent_ctas(
             prepare<pw_int, pw_friction, SEEDED>(), yb::SWEEP_THREADS, max_ctas);
+        if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::SWEEP_THREADS, yb::SWEEP_SMEM, s>>>(d_n, n_max, pos4,
                 aux, cube_sorted, sort.offset, cube_size, grid_size, n_cubes,

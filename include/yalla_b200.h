@@ -108,6 +108,13 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
 int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     int n_steps, float* h_out, int capacity, int* n_out);
 
+/* Time the dominant kernel (the pairwise sweep) with CUDA events on the
+ * launching stream: enable, run steps, then read the accumulated milliseconds
+ * and the number of sweep launches since the last read. Product library only
+ * (YB_ENOSYS elsewhere); used by bench.py for the roofline line. */
+int yb_sim_profile_sweeps(yb_sim* sim, int enable);
+int yb_sim_read_sweep_profile(yb_sim* sim, float* total_ms, int* launches);
+
 /* Current cell count (blocking read of d_n: Solution::get_d_n). */
 int yb_sim_n(yb_sim* sim, int* n_out);
 int yb_sim_sync(yb_sim* sim);

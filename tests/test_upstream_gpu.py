@@ -1,0 +1,31 @@
+"""The reference's own test programs (tests/*.cu in /root/reference), compiled
+UNCHANGED against this repo's include/ by yalla_b200.build.build_upstream_tests
+and run on the GPU. They are the drop-in proof for the header API: the three
+files that no longer compile against the reference's own headers
+do compile here, because Generic_forces also accepts the two-argument form and
+the polarity functions accept points.
+"""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "tests", "_bin")
+TESTS = ["test_dtypes", "test_solvers", "test_links", "test_polarity",
+         "test_inits", "test_vtk"]
+
+
+@pytest.mark.parametrize("name", TESTS)
+def test_upstream_suite(name, tmp_path):
+    binary = os.path.join(BIN, name)
+    if not os.path.exists(binary):
+        pytest.skip(f"{binary} was not built (needs /root/reference at build time)")
+    env = dict(os.environ, YALLA_B200_SEED="7")
+    result = subprocess.run([binary], cwd=tmp_path, capture_output=True, text=True,
+                            timeout=600, env=env)
+    assert "ALL TESTS PASSED" in result.stdout, result.stdout[-2000:] + result.stderr[-2000:]
+    assert result.returncode == 0

@@ -60,6 +60,9 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_float,
                                         ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_int, _c_int_p]),
+    "yb_sim_profile_sweeps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_sim_read_sweep_profile": (ctypes.c_int, [ctypes.c_void_p, _c_float_p,
+                                                 _c_int_p]),
     "yb_sim_n": (ctypes.c_int, [ctypes.c_void_p, _c_int_p]),
     "yb_sim_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "yb_grid_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
@@ -250,6 +253,19 @@ class Sim:
             self.handle, X_in.ctypes.data, len(X_in), dt, n_steps,
             X_out.ctypes.data, len(X_out), ctypes.byref(n)), "step_host")
         return n.value
+
+    def profile_sweeps(self, enable=True):
+        self.lib.check(self.lib.cdll.yb_sim_profile_sweeps(
+            self.handle, int(enable)), "profile_sweeps")
+
+    def read_sweep_profile(self):
+        """-> (total milliseconds in sweep kernels, number of sweep launches)"""
+        ms = ctypes.c_float()
+        launches = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_sim_read_sweep_profile(
+            self.handle, ctypes.byref(ms), ctypes.byref(launches)),
+            "read_sweep_profile")
+        return ms.value, launches.value
 
     def n(self):
         n = ctypes.c_int()

@@ -64,6 +64,14 @@ struct yb_sim {
     // model tracks it on the host (growing models), else -1.
     virtual int step(float dt) = 0;
     virtual int current_n() = 0;
+    virtual int profile_sweeps(int enable)
+    {
+        return fail(YB_ENOSYS, "sweep profiling needs the product library");
+    }
+    virtual int read_sweep_profile(float* total_ms, int* launches)
+    {
+        return fail(YB_ENOSYS, "sweep profiling needs the product library");
+    }
 };
 
 namespace {
@@ -115,6 +123,18 @@ struct Sim_base : yb_sim {
         return check_cuda("get_velocities");
     }
     int current_n() override { return n_host = cells.get_d_n(); }
+#ifdef YALLA_B200
+    int profile_sweeps(int enable) override
+    {
+        cells.profile_sweeps(enable != 0);
+        return YB_OK;
+    }
+    int read_sweep_profile(float* total_ms, int* launches) override
+    {
+        cells.read_sweep_profile(total_ms, launches);
+        return YB_OK;
+    }
+#endif
 
     int set_fix(const std::string& name, double value)
     {
@@ -577,6 +597,16 @@ int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     if (status != YB_OK) return status;
     for (int k = 0; k < n_steps; k++) sim->step(dt);
     return sim->get_state(h_out, capacity, n_out);
+}
+
+int yb_sim_profile_sweeps(yb_sim* sim, int enable)
+{
+    return sim->profile_sweeps(enable);
+}
+
+int yb_sim_read_sweep_profile(yb_sim* sim, float* total_ms, int* launches)
+{
+    return sim->read_sweep_profile(total_ms, launches);
 }
 
 int yb_sim_n(yb_sim* sim, int* n_out)
