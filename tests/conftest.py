@@ -8,6 +8,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))  # make_golden: the case list
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import yalla_b200 as yb  # noqa: E402
 

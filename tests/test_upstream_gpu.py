@@ -1,5 +1,5 @@
 """The reference's own test programs (tests/*.cu in /root/reference), compiled
-UNCHANGED against this repo's include/ by yalla_b200.build.build_upstream_tests
+UNCHANGED against this repo's include/ by oracle/build_checkers.py
 and run on the GPU. They are the drop-in proof for the header API: the three
 files that no longer compile against the reference's own headers
 do compile here, because Generic_forces also accepts the two-argument form and

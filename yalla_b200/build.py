@@ -1,29 +1,21 @@
-"""Build recipes (nvcc cross-compiles sm_100a without a GPU).
+"""Build recipe of the product library (nvcc cross-compiles sm_100a without a
+GPU).
 
-    python -m yalla_b200.build            product library
-    python -m yalla_b200.build all        + oracle, reference library, upstream
-                                            test binaries (where /root/reference
-                                            is mounted)
+    python -m yalla_b200.build
 
-Everything is built in-tree so that it travels with the repository snapshot:
-    yalla_b200/_lib/libyalla_b200.so   the product (include/ + csrc/capi.cu)
-    oracle/_build/libyalla_oracle.so   CPU oracle               (oracle/Makefile)
-    oracle/_ref/libyalla_ref.so        reference headers, sm_100a (oracle/Makefile)
-    tests/_bin/<test>                  the reference's own tests/*.cu compiled
-                                       UNCHANGED against include/ (drop-in proof)
+Built in-tree so that it travels with the repository snapshot:
+    yalla_b200/_lib/libyalla_b200.so   include/ + yalla_b200/csrc/capi.cu
+
+The checkers (CPU oracle, reference build, upstream test programs) are test
+infrastructure and have their own recipes in oracle/build_checkers.py.
 """
 import os
-import shutil
 import subprocess
 import sys
-from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REFERENCE = os.environ.get("YALLA_REFERENCE", "/root/reference")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo"] + ARCH
-UPSTREAM_TESTS = ["test_dtypes", "test_solvers", "test_links", "test_polarity",
-                  "test_inits", "test_vtk"]
 
 
 def _run(cmd, **kw):
@@ -63,60 +55,5 @@ def build_product(force=False):
     return out
 
 
-def build_oracle():
-    _run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
-    return os.path.join(ROOT, "oracle", "_build", "libyalla_oracle.so")
-
-
-def have_reference():
-    return os.path.isdir(os.path.join(REFERENCE, "include"))
-
-
-def build_reference():
-    """The reference's own headers -> oracle/_ref (only where it is mounted)."""
-    if not have_reference():
-        return None
-    _run(["make", "-C", os.path.join(ROOT, "oracle"), "ref",
-          f"REFERENCE={REFERENCE}"])
-    return os.path.join(ROOT, "oracle", "_ref", "libyalla_ref.so")
-
-
-def build_upstream_tests():
-    """Compile the reference's tests/*.cu, unmodified, against include/.
-
-    The sources include "../include/x.cuh" relative to themselves, so they are
-    symlinked into a staging tree whose include/ is this repo's. Nothing is
-    copied into the repository; only the binaries land in tests/_bin/.
-    """
-    if not have_reference():
-        return []
-    stage = os.path.join(ROOT, "build", "upstream_stage")
-    shutil.rmtree(stage, ignore_errors=True)
-    os.makedirs(os.path.join(stage, "tests"))
-    os.symlink(os.path.join(ROOT, "include"), os.path.join(stage, "include"))
-    for name in os.listdir(os.path.join(REFERENCE, "tests")):
-        os.symlink(os.path.join(REFERENCE, "tests", name),
-                   os.path.join(stage, "tests", name))
-    out_dir = os.path.join(ROOT, "tests", "_bin")
-    os.makedirs(out_dir, exist_ok=True)
-
-    def compile_one(test):
-        out = os.path.join(out_dir, test)
-        if _newer(out, [os.path.join(ROOT, "include")]):
-            return out
-        _run(["nvcc"] + NVCC_FLAGS + ["-o", out, f"tests/{test}.cu"], cwd=stage)
-        return out
-
-    with ThreadPoolExecutor(max_workers=6) as pool:
-        return list(pool.map(compile_one, UPSTREAM_TESTS))
-
-
-def build_all():
-    with ThreadPoolExecutor(max_workers=4) as pool:
-        jobs = [pool.submit(build_product), pool.submit(build_oracle),
-                pool.submit(build_reference), pool.submit(build_upstream_tests)]
-        return [job.result() for job in jobs]
-
-
 if __name__ == "__main__":
-    print(build_all() if "all" in sys.argv[1:] else build_product(force=True))
+    print(build_product(force=True))
