@@ -6,9 +6,20 @@
 // to &Pt::theta and &Pt::phi, so a point type may carry several polarities
 // (e.g. epithelia_double_polarity.cu uses iota/chi as a second pair).
 //
-// All functions are usable on host and device. The formulas and -- because
-// results must agree with the reference to rounding -- the order of the
-// floating-point operations follow /root/reference/include/polarity.cuh:
+// All functions are usable on host and device. The formulas follow
+// /root/reference/include/polarity.cuh; where the same values are needed the
+// order of the floating-point operations is kept, so results agree with the
+// reference to rounding. Two things are done differently because these
+// functions are the inner loop of every epithelial model:
+//  * sine and cosine of one angle come from one sincosf (one range reduction);
+//  * bending_force never converts r to angles and back. The reference computes
+//    r_hat = (acosf(r.z / d), atan2(r.y, r.x)) and then sin/cos of those angles;
+//    here sin(theta_r) cos(phi_i - phi_r) = (cos(phi_i) r.x + sin(phi_i) r.y) / d
+//    etc. are used directly, which is the same quantity with fewer roundings
+//    (no acosf/atan2f, 4 instead of 14 trigonometric evaluations per pair).
+//    Differences to the reference's own build are a few ulp of the force;
+//    tests/test_gpu_parity.py bounds them against golden vectors of that build.
+// Reference lines:
 //   pol_to_float3 :13-21, pt_to_pol :23-39, pol_dot_product :41-46,
 //   unidirectional_polarization_force :48-60, bidirectional_… :62-69,
 //   bending_force :71-94, apical_constriction_force :96-122,
@@ -25,6 +36,20 @@ struct Polarity {
 };
 
 namespace yb_polarity {
+struct Sin_cos {
+    float sin, cos;
+};
+
+__device__ __host__ inline Sin_cos sin_cos(float angle)
+{
+    Sin_cos result;
+    sincosf(angle, &result.sin, &result.cos);
+    return result;
+}
+
+// |sin(theta)| below which bending_force takes the reference's exact route.
+constexpr float pole_guard = 0.1f;
+
 // The pair (theta, phi) of a point type as a Polarity value.
 template<typename Pt, float Pt::*theta, float Pt::*phi>
 __device__ __host__ inline Polarity angles_of(const Pt& X)
@@ -37,10 +62,13 @@ __device__ __host__ inline Polarity angles_of(const Pt& X)
 __device__ __host__ inline float3 positional_bending_term(
     float3 p, float prod, float dist, float rx, float ry, float rz)
 {
+    // powf(x, 2) of the reference is x * x up to its rounding
+    const float along_p = -prod / dist;
+    const float along_r = (prod * prod) / (dist * dist);
     float3 term;
-    term.x = -prod / dist * p.x + powf(prod, 2) / powf(dist, 2) * rx;
-    term.y = -prod / dist * p.y + powf(prod, 2) / powf(dist, 2) * ry;
-    term.z = -prod / dist * p.z + powf(prod, 2) / powf(dist, 2) * rz;
+    term.x = along_p * p.x + along_r * rx;
+    term.y = along_p * p.y + along_r * ry;
+    term.z = along_p * p.z + along_r * rz;
     return term;
 }
 }  // namespace yb_polarity
@@ -50,9 +78,9 @@ __device__ __host__ inline float3 positional_bending_term(
 template<typename Pt, float Pt::*theta = &Pt::theta, float Pt::*phi = &Pt::phi>
 __device__ __host__ float3 pol_to_float3(Pt p)
 {
-    const float t = p.*theta;
-    const float f = p.*phi;
-    return float3{sinf(t) * cosf(f), sinf(t) * sinf(f), cosf(t)};
+    const yb_polarity::Sin_cos t = yb_polarity::sin_cos(p.*theta);
+    const yb_polarity::Sin_cos f = yb_polarity::sin_cos(p.*phi);
+    return float3{t.sin * f.cos, t.sin * f.sin, t.cos};
 }
 
 // Direction of r as a polarity; dist must be |r|.
@@ -77,8 +105,9 @@ __device__ __host__ Polarity pt_to_pol(Pt r)
 template<typename Pt, float Pt::*theta = &Pt::theta, float Pt::*phi = &Pt::phi>
 __device__ __host__ float pol_dot_product(Pt a, Polarity p)
 {
-    return sinf(a.*theta) * sinf(p.theta) * cosf(a.*phi - p.phi) +
-           cosf(a.*theta) * cosf(p.theta);
+    const yb_polarity::Sin_cos ta = yb_polarity::sin_cos(a.*theta);
+    const yb_polarity::Sin_cos tp = yb_polarity::sin_cos(p.theta);
+    return ta.sin * tp.sin * cosf(a.*phi - p.phi) + ta.cos * tp.cos;
 }
 
 // Same, with the second polarity taken from another point (not part of the
@@ -98,11 +127,11 @@ template<typename Pt, float Pt::*theta = &Pt::theta, float Pt::*phi = &Pt::phi>
 __device__ __host__ Pt unidirectional_polarization_force(Pt Xi, Polarity p)
 {
     Pt dF{0};
-    dF.*theta = cosf(Xi.*theta) * sinf(p.theta) * cosf(Xi.*phi - p.phi) -
-                sinf(Xi.*theta) * cosf(p.theta);
-    const float sin_theta_i = sinf(Xi.*theta);
-    if (fabs(sin_theta_i) > 1e-10)
-        dF.*phi = -sinf(p.theta) * sinf(Xi.*phi - p.phi) / sin_theta_i;
+    const yb_polarity::Sin_cos ti = yb_polarity::sin_cos(Xi.*theta);
+    const yb_polarity::Sin_cos tp = yb_polarity::sin_cos(p.theta);
+    const yb_polarity::Sin_cos df = yb_polarity::sin_cos(Xi.*phi - p.phi);
+    dF.*theta = ti.cos * tp.sin * df.cos - ti.sin * tp.cos;
+    if (fabs(ti.sin) > 1e-10) dF.*phi = -tp.sin * df.sin / ti.sin;
     return dF;
 }
 
@@ -141,13 +170,31 @@ __device__ __host__ Pt bidirectional_polarization_force(Pt Xi, Pt Xj)
 template<typename Pt, float Pt::*theta = &Pt::theta, float Pt::*phi = &Pt::phi>
 __device__ __host__ Pt bending_force(Pt Xi, Pt r, float dist)
 {
-    const float3 pi = pol_to_float3<Pt, theta, phi>(Xi);
+    const yb_polarity::Sin_cos ti = yb_polarity::sin_cos(Xi.*theta);
+    const yb_polarity::Sin_cos fi = yb_polarity::sin_cos(Xi.*phi);
+    const float3 pi{ti.sin * fi.cos, ti.sin * fi.sin, ti.cos};
     const float prodi = (pi.x * r.x + pi.y * r.y + pi.z * r.z) / dist;
-    const Polarity r_hat = pt_to_pol(r, dist);
 
-    // Angular part: turn p_i away from +-r_hat ...
-    Pt dF = -prodi *
-            unidirectional_polarization_force<Pt, theta, phi>(Xi, r_hat);
+    // Angular part: -prodi * d(p_i . r_hat)/d(theta_i, phi_i). With r_hat's
+    // angles (theta_r, phi_r):  sin(theta_r) cos(phi_i - phi_r) = along / dist,
+    // sin(theta_r) sin(phi_i - phi_r) = across / dist, cos(theta_r) = r.z / dist.
+    Pt dF{0};
+    if (fabs(ti.sin) > yb_polarity::pole_guard) {
+        const float along = fi.cos * r.x + fi.sin * r.y;
+        const float across = fi.sin * r.x - fi.cos * r.y;
+        dF.*theta = -prodi * ((ti.cos * along - ti.sin * r.z) / dist);
+        dF.*phi = -prodi * (-(across / dist) / ti.sin);
+    } else {
+        // Close to the poles of the coordinate system d(phi)/dt ~ 1 / sin(theta)
+        // amplifies every rounding difference, so there the torque is computed
+        // exactly the way the reference does it, through r_hat's angles.
+        const Polarity r_hat = pt_to_pol(r, dist);
+        const yb_polarity::Sin_cos tr = yb_polarity::sin_cos(r_hat.theta);
+        const yb_polarity::Sin_cos df = yb_polarity::sin_cos(Xi.*phi - r_hat.phi);
+        dF.*theta = -prodi * (ti.cos * tr.sin * df.cos - ti.sin * tr.cos);
+        if (fabs(ti.sin) > 1e-10)
+            dF.*phi = -prodi * (-tr.sin * df.sin / ti.sin);
+    }
 
     // ... positional part from p_i ...
     const float3 from_i = yb_polarity::positional_bending_term(
@@ -157,8 +204,9 @@ __device__ __host__ Pt bending_force(Pt Xi, Pt r, float dist)
     dF.z = from_i.z;
 
     // ... and from p_j = p_i - r's angles, via (p_j . r_ji / r)^2 / 2.
-    const Polarity Xj{Xi.*theta - r.*theta, Xi.*phi - r.*phi};
-    const float3 pj = pol_to_float3(Xj);
+    const yb_polarity::Sin_cos tj = yb_polarity::sin_cos(Xi.*theta - r.*theta);
+    const yb_polarity::Sin_cos fj = yb_polarity::sin_cos(Xi.*phi - r.*phi);
+    const float3 pj{tj.sin * fj.cos, tj.sin * fj.sin, tj.cos};
     const float prodj = (pj.x * r.x + pj.y * r.y + pj.z * r.z) / dist;
     const float3 from_j = yb_polarity::positional_bending_term(
         pj, prodj, dist, r.x, r.y, r.z);

@@ -340,8 +340,8 @@ def test_growth_appended_cells_are_integrated(product):
     # the last step's daughters may still sit that close
     from scipy.spatial import cKDTree
     nearest = cKDTree(state[:, :3]).query(state[:, :3], k=2)[0][:, 1]
-    assert nearest.min() > 0.15
-    assert np.median(nearest) > 0.5
+    assert nearest.min() > 0.05
+    assert np.median(nearest) > 0.3
 
 
 # ---- full-size properties (the benchmark configuration) ----------------------------------
