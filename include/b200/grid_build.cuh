@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) publish_grid(const int n,
 
 // Launch width for grid-stride kernels over n_max elements: enough CTAs to
 // fill the machine a few times over, never more than the data needs.
-inline int stride_grid(int n_max, int threads, int n_sms, int ctas_per_sm = 8)
+inline int stride_grid(int n_max, int threads, int n_sms, int ctas_per_sm = 32)
 {
     const int wanted = ceil_div(n_max > 0 ? n_max : 1, threads);
     const int cap = n_sms * ctas_per_sm;

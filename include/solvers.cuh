@@ -239,6 +239,7 @@ public:
         YB_CUDA(cudaMalloc(&d_partials, 3 * max_sweep_ctas * sizeof(float)));
         YB_CUDA(cudaStreamCreateWithFlags(
             &capture_stream, cudaStreamNonBlocking));
+        YB_CUDA(cudaMallocHost(&h_n_pinned, sizeof(int)));
     }
     Heun_solver(const Heun_solver&) = delete;
     Heun_solver& operator=(const Heun_solver&) = delete;
@@ -246,6 +247,7 @@ public:
     {
         cudaStreamSynchronize(stream);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        cudaFreeHost(h_n_pinned);
         cudaStreamDestroy(capture_stream);
         cudaFree(d_partials);
         cudaFree(d_ctl);
@@ -324,10 +326,12 @@ protected:
 
     int get_d_n()
     {
-        int n;
+        // through a pinned word: a plain 4-byte cudaMemcpy to pageable memory
+        // costs several times the round trip
         YB_CUDA(cudaMemcpyAsync(
-            &n, d_n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            h_n_pinned, d_n, sizeof(int), cudaMemcpyDeviceToHost, stream));
         YB_CUDA(cudaStreamSynchronize(stream));
+        const int n = *h_n_pinned;
         assert(n <= n_max);
         return n;
     }
@@ -396,6 +400,7 @@ private:
     int max_sweep_ctas;
     cudaStream_t capture_stream;
     std::vector<yb::Step_graph> graphs;
+    int* h_n_pinned = nullptr;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
 

@@ -60,9 +60,10 @@ struct yb_sim {
     {
         return fail(YB_EINVAL, "model has no links");
     }
-    // One model step; returns the cell count at the start of the step if the
-    // model tracks it on the host (growing models), else -1.
+    // One model step (asynchronous).
     virtual int step(float dt) = 0;
+    // Device address of the current cell count (for asynchronous snapshots).
+    virtual const int* count_on_device() = 0;
     virtual int current_n() = 0;
     virtual int profile_sweeps(int enable)
     {
@@ -123,6 +124,7 @@ struct Sim_base : yb_sim {
         return check_cuda("get_velocities");
     }
     int current_n() override { return n_host = cells.get_d_n(); }
+    const int* count_on_device() override { return cells.d_n; }
 #ifdef YALLA_B200
     int profile_sweeps(int enable) override
     {
@@ -179,7 +181,7 @@ struct Spring_sim : Sim_base<float3, Solver> {
     int step(float dt) override
     {
         this->cells.template take_step<force>(dt);
-        return -1;
+        return 0;
     }
 };
 
@@ -214,7 +216,7 @@ struct Protrusion_sim : Sim_base<float3, Grid_solver> {
         auto pull = [this](const int n, const float3* __restrict__ d_X,
                         float3* d_dX) { link_forces(links, d_X, d_dX); };
         cells.take_step<relu_force<float3>>(dt, pull);
-        return -1;
+        return 0;
     }
 };
 
@@ -232,7 +234,7 @@ struct Epithelium_sim : Sim_base<Po_cell, Grid_solver> {
     int step(float dt) override
     {
         cells.take_step<models::layer_force, friction_on_background>(dt);
-        return -1;
+        return 0;
     }
 };
 
@@ -307,6 +309,7 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
 // ---- Po_cell growth ------------------------------------------------------------------
 struct Growth_sim : Typed_sim<Po_cell> {
     curandState* d_state = nullptr;
+    int* d_n_at_launch = nullptr;
     float prolif_rate = 0.006f, mean_dist = 0.75f;
     int seed = 2;
     bool seeded = false;
@@ -315,8 +318,13 @@ struct Growth_sim : Typed_sim<Po_cell> {
         : Typed_sim<Po_cell>{n_max, grid_size, cube_size}
     {
         cudaMalloc(&d_state, sizeof(curandState) * size_t(n_max));
+        cudaMalloc(&d_n_at_launch, sizeof(int));
     }
-    ~Growth_sim() override { cudaFree(d_state); }
+    ~Growth_sim() override
+    {
+        cudaFree(d_n_at_launch);
+        cudaFree(d_state);
+    }
     int set_param(const std::string& name, double value) override
     {
         if (name == "prolif_rate") {
@@ -343,13 +351,15 @@ struct Growth_sim : Typed_sim<Po_cell> {
         bind();
         auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
                              Po_cell* d_dX) { reset_counters(n); };
-        const int n = cells.get_d_n();
         cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
-        if (prolif_rate > 0 && n > 0)
-            models::proliferate<<<(n + 128 - 1) / 128, 128>>>(prolif_rate,
-                mean_dist, n, n_max, d_state, cells.d_X, cells.d_old_v,
-                cells.d_n);
-        return n;
+        if (prolif_rate > 0) {
+            // sized for the capacity; the kernel reads the live count itself
+            models::snapshot_count<<<1, 1>>>(cells.d_n, d_n_at_launch);
+            models::proliferate<<<(n_max + 128 - 1) / 128, 128>>>(prolif_rate,
+                mean_dist, n_max, d_state, cells.d_X, cells.d_old_v, cells.d_n,
+                d_n_at_launch);
+        }
+        return 0;
     }
 };
 
@@ -369,7 +379,7 @@ struct Branching_sim : Typed_sim<models::Cell> {
         auto reset_nbs = [this](const int n, const models::Cell* __restrict__ d_X,
                              models::Cell* d_dX) { reset_counters(n); };
         cells.take_step<models::epi_turing_mes_noturing>(dt, reset_nbs);
-        return -1;
+        return 0;
     }
 };
 
@@ -571,13 +581,17 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
     cudaEvent_t start, stop;
     cudaEventCreate(&start);
     cudaEventCreate(&stop);
-    long long updates = 0;
-    const int n_start = sim->current_n();
+    // cell count at the start of every step, snapshotted asynchronously into
+    // pinned memory so that counting does not serialise the steps
+    int* h_counts = nullptr;
+    cudaMallocHost(&h_counts, sizeof(int) * static_cast<size_t>(n_steps + 1));
+    const int* d_count = sim->count_on_device();
     cudaDeviceSynchronize();
     cudaEventRecord(start, 0);
     for (int k = 0; k < n_steps; k++) {
-        const int n = sim->step(dt);
-        updates += n >= 0 ? n : n_start;
+        cudaMemcpyAsync(
+            h_counts + k, d_count, sizeof(int), cudaMemcpyDeviceToHost, 0);
+        sim->step(dt);
     }
     cudaEventRecord(stop, 0);
     cudaEventSynchronize(stop);
@@ -585,6 +599,9 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
     cudaEventElapsedTime(&ms, start, stop);
     cudaEventDestroy(start);
     cudaEventDestroy(stop);
+    long long updates = 0;
+    for (int k = 0; k < n_steps; k++) updates += h_counts[k];
+    cudaFreeHost(h_counts);
     if (ms_out) *ms_out = ms;
     if (cell_updates_out) *cell_updates_out = updates;
     return check_cuda("yb_sim_step_timed");

@@ -114,9 +114,20 @@ __device__ Po_cell relu_w_epithelium(
 // Cell division, examples/passive_growth.cu:59-91: mesenchymal cells divide
 // at `rate`, epithelial cells when they have more mesenchymal than epithelial
 // neighbours; the daughter is appended at slot atomicAdd(d_n_cells, 1).
-__global__ void proliferate(float rate, float mean_dist, int n_cells, int n_max,
-    curandState* d_state, Po_cell* d_X, float3* d_old_v, int* d_n_cells)
+// snapshot_count freezes the count first, so that all blocks agree on which
+// cells existed when the step began.
+__global__ void snapshot_count(const int* d_n_cells, int* d_n_at_launch)
 {
+    *d_n_at_launch = *d_n_cells;
+}
+
+// The number of cells at launch is read from d_n_cells by the first thread of
+// every block (no host round trip to size the launch); blocks beyond it exit.
+__global__ void proliferate(float rate, float mean_dist, int n_max,
+    curandState* d_state, Po_cell* d_X, float3* d_old_v, int* d_n_cells,
+    const int* d_n_at_launch)
+{
+    const int n_cells = *d_n_at_launch;
     auto i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cells) return;  // Dividing new cells is problematic!
 
