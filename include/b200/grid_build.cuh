@@ -64,6 +64,12 @@ struct Step_ctl {
     int n_snapshot;       // n used by the step in flight (diagnostic)
     int pad0, pad1;
     float drift[2][4];    // per Heun stage: mean (or fixed-point) dX.xyz
+    // Domain decomposition (b200/slab.cuh): cells with an id >= n_owned are
+    // ghosts -- neighbours only. 0 means "all cells are owned".
+    int n_owned;
+    int external_drift;   // 1: the sweep leaves drift[] alone (set by the host)
+    int pad2, pad3;
+    float drift_sum[2][4];  // per stage: sum of dX.xyz over owned cells, count
 };
 
 // Set by the solver around the generic-forces callback, so that forces called

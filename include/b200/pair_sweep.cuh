@@ -246,11 +246,21 @@ __device__ __forceinline__ void finish_drift(float3 my_partial,
     }
     const float3 total = block_sum3<THREADS>(x, y, z, s_red);
     if (threadIdx.x == 0) {
-        const float inv_n = static_cast<float>(1. / static_cast<float>(n));
-        float3 mean{0.f, 0.f, 0.f};
-        if (n > 0) mean = float3{total.x * inv_n, total.y * inv_n, total.z * inv_n};
-        publish_drift(mean, n > 0 ? drift_mode : DRIFT_MEAN, fix_point, d_dX,
-            stage, ctl);
+        // with ghosts present only the owned cells count
+        const int owned = ctl->n_owned > 0 && ctl->n_owned < n ? ctl->n_owned : n;
+        ctl->drift_sum[stage][0] = total.x;
+        ctl->drift_sum[stage][1] = total.y;
+        ctl->drift_sum[stage][2] = total.z;
+        ctl->drift_sum[stage][3] = static_cast<float>(owned);
+        if (!ctl->external_drift) {
+            const float inv_n =
+                static_cast<float>(1. / static_cast<float>(owned));
+            float3 mean{0.f, 0.f, 0.f};
+            if (owned > 0)
+                mean = float3{total.x * inv_n, total.y * inv_n, total.z * inv_n};
+            publish_drift(mean, owned > 0 ? drift_mode : DRIFT_MEAN, fix_point,
+                d_dX, stage, ctl);
+        }
         ctl->sweep_blocks_done = 0;
     }
 }
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
     const int n = live_cells(d_n, n_max);
     const int n_chunks = ceil_div(n, SWEEP_THREADS);
     const float reach2 = cube_size * cube_size * SWEEP_PREFILTER_SLACK;
+    const int n_owned = ctl->n_owned > 0 ? ctl->n_owned : n_max;
 
     if (t == 0) mbar_init(&s_bar, 1);
     __syncthreads();
@@ -333,8 +344,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
         const int total = s_row_v[SWEEP_ROWS];
 
         const int my_id = __float_as_int(me.w);
+        // ghost cells (domain decomposition) are candidates, never subjects
+        const bool owned = live && my_id < n_owned;
         Pt Xi{0};
-        if (live) Xi = assemble_pt<Pt>(me, aux + size_t(k) * L::aux_vec4);
+        if (owned) Xi = assemble_pt<Pt>(me, aux + size_t(k) * L::aux_vec4);
         Pt F{0};
         float3 sum_v{0.f, 0.f, 0.f};
         float sum_friction = 0.f;
@@ -370,7 +383,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
             // -- phase 1 (scan) and phase 2 (interact). One pass unless a list
             //    overflows; then the scan resumes where it stopped.
             int r0 = 0, a0 = -1;
-            bool pending = live;
+            bool pending = owned;
             while (pending) {
                 int listed = 0;
                 pending = false;
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
 
         // -- epilogue: dX (+)= F, friction term, drift partial
         float3 mine{0.f, 0.f, 0.f};
-        if (live) {
+        if (owned) {
             Pt dX = F;
             if (SEEDED) {
                 dX = load_pt_rw(d_dX, my_id);

@@ -289,6 +289,52 @@ public:
     // default stream, like every launch in a ya||a model).
     cudaStream_t stream = 0;
 
+    // ---- Extension: building blocks for domain decomposition ------------------
+    // One solver integrates the cells of one spatial domain. Cells [0, n_owned)
+    // are its own; cells [n_owned, n_total) are GHOSTS, copies of neighbouring
+    // domains' boundary cells that act as interaction partners only. The drift
+    // (mean force) is global, so the sweep leaves its local sum in device
+    // memory, the caller reduces it over all domains (NCCL) and hands the mean
+    // back. yalla_b200/dd.py drives these per stage; see DESIGN.md section 6.
+    void dd_set_counts(int n_owned, int n_total)
+    {
+        assert(n_owned <= n_total && n_total <= n_max);
+        const int header[2] = {n_owned, 1};  // n_owned, external_drift
+        YB_CUDA(cudaMemcpyAsync(&d_ctl->n_owned, header, sizeof(header),
+            cudaMemcpyHostToDevice, stream));
+        YB_CUDA(cudaMemcpyAsync(
+            d_n, &n_total, sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
+    // Positions the given stage works on (stage 0: X, stage 1: X1), old
+    // velocities, and the per-stage sums {sum dX.x, .y, .z, n_owned}.
+    Pt* dd_positions(int stage) { return stage == 0 ? d_X : d_X1; }
+    float3* dd_velocities() { return d_old_v; }
+    const float* dd_drift_sum(int stage) { return d_ctl->drift_sum[stage]; }
+    // Grid build + pairwise sweep of one stage over owned + ghost cells.
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
+    void dd_forces(int stage)
+    {
+        Computer<Pt>::template pwints<pw_int, pw_friction, false>(stream, d_n,
+            stage == 0 ? d_X : d_X1, d_old_v, stage == 0 ? d_dX : d_dX1,
+            d_partials, max_sweep_ctas, stage, yb::DRIFT_MEAN, 0, d_ctl, false);
+        YB_CUDA(cudaGetLastError());
+    }
+    // Predictor (stage 0) or corrector (stage 1) with the global drift d_mean
+    // (3 floats in device memory).
+    void dd_update(int stage, float dt, const float* d_mean)
+    {
+        YB_CUDA(cudaMemcpyAsync(d_ctl->drift[stage], d_mean, 3 * sizeof(float),
+            cudaMemcpyDeviceToDevice, stream));
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        if (stage == 0)
+            yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+        else
+            yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
+                d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+        YB_CUDA(cudaGetLastError());
+    }
+
     // Extension: time the pairwise sweep kernels with CUDA events on the
     // launching stream (bench.py's roofline needs the dominant kernel's own
     // duration). While enabled, steps are issued directly instead of replayed

@@ -115,6 +115,31 @@ int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
 int yb_sim_profile_sweeps(yb_sim* sim, int enable);
 int yb_sim_read_sweep_profile(yb_sim* sim, float* total_ms, int* launches);
 
+/* ---- domain decomposition building blocks ------------------------------------
+ * For tissues larger than one GPU the domain is cut into slabs, one solver per
+ * slab and GPU (yalla_b200/dd.py; not part of the reference, which is single-
+ * GPU). A solver then holds its n_owned cells followed by n_ghost GHOST cells --
+ * copies of the neighbouring slabs' boundary cells, interaction partners only.
+ * Pointers are in the library's memory space (device memory for the CUDA
+ * libraries, host memory for the CPU oracle). Grid models without per-id
+ * property arrays only ("relu_grid", "spring_grid", "epithelium").
+ *
+ * yb_dd_load    stage 0: replace the owned state (positions/extras X, old
+ *               velocities v) and append the ghosts; stage 1: keep the owned
+ *               predictor positions, append the ghosts' predictor positions.
+ * yb_dd_forces  grid build + pairwise sweep of the stage; writes
+ *               {sum dX.x, sum dX.y, sum dX.z, n_owned} of the OWNED cells to
+ *               sums4 -- to be summed over all domains by the caller.
+ * yb_dd_update  predictor (stage 0) / corrector (stage 1) with the global mean
+ *               force mean3 = sum / n removed (solvers.cuh:241-255, 266-274).
+ * yb_dd_read    copy n owned cells of X (0), X1 (1) or old velocities (2). */
+int yb_dd_load(yb_sim* sim, int stage, const float* X_owned,
+    const float* v_owned, int n_owned, const float* X_ghost,
+    const float* v_ghost, int n_ghost);
+int yb_dd_forces(yb_sim* sim, int stage, float* sums4);
+int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3);
+int yb_dd_read(yb_sim* sim, int which, float* out, int n);
+
 /* Current cell count (blocking read of d_n: Solution::get_d_n). */
 int yb_sim_n(yb_sim* sim, int* n_out);
 int yb_sim_sync(yb_sim* sim);

@@ -402,6 +402,11 @@ struct yb_sim {
     virtual int set_links(const int*, int) = 0;
     virtual int step(float dt) = 0;
     virtual int current_n() const = 0;
+    virtual int dd_load(int, const float*, const float*, int, const float*,
+        const float*, int) = 0;
+    virtual int dd_forces(int, float*) = 0;
+    virtual int dd_update(int, float, const float*) = 0;
+    virtual int dd_read(int, float*, int) = 0;
 };
 
 namespace {
@@ -422,6 +427,7 @@ struct Sim : yb_sim {
     std::vector<int> links;  // pairs
     bool fix_com = true, fix_com_z = false;
     int fix_point = 0;
+    int n_owned = 0;  // domain decomposition: cells >= n_owned are ghosts
 
     Sim(int n_max, Solver solver, Force<L> force, Friction friction,
         int grid_size, float cube_size)
@@ -569,6 +575,7 @@ struct Sim : yb_sim {
 #pragma omp parallel for schedule(dynamic, 256)
             for (int s = 0; s < n; s++) {
                 const int i = grid.point_id[s];
+                if (n_owned > 0 && i >= n_owned) continue;  // ghost
                 const Pt<L> Xi = P[i];
                 Pt<L> F = zero<L>();
                 F3 sv{0, 0, 0};
@@ -618,8 +625,71 @@ struct Sim : yb_sim {
         return total / float(n);
     }
 
+    // ---- domain decomposition building blocks (host pointers) ---------------
+    int dd_load(int stage, const float* X_owned, const float* v_owned,
+        int owned, const float* X_ghost, const float* v_ghost,
+        int n_ghost) override
+    {
+        if (solver != GRID || counts_neighbours || has_links)
+            return fail(YB_ENOSYS, "domain decomposition needs a plain Grid model");
+        if (owned + n_ghost > capacity) return fail(YB_EINVAL, "n > n_max");
+        std::vector<Pt<L>>& P = stage == 0 ? X : X1;
+        if (stage == 0) {
+            memcpy(P.data(), X_owned, sizeof(Pt<L>) * size_t(owned));
+            memcpy(old_v.data(), v_owned, sizeof(F3) * size_t(owned));
+        }
+        if (n_ghost > 0) {
+            memcpy(P.data() + owned, X_ghost, sizeof(Pt<L>) * size_t(n_ghost));
+            memcpy(old_v.data() + owned, v_ghost, sizeof(F3) * size_t(n_ghost));
+        }
+        n_owned = owned;
+        n = owned + n_ghost;
+        return YB_OK;
+    }
+    int dd_forces(int stage, float* sums4) override
+    {
+        std::vector<Pt<L>>& dP = stage == 0 ? dX : dX1;
+        derivative(stage == 0 ? X : X1, dP);
+        double acc[3] = {0, 0, 0};
+        for (int i = 0; i < n_owned; i++)
+            for (int k = 0; k < 3; k++) acc[k] += dP[i].v[k];
+        for (int k = 0; k < 3; k++) sums4[k] = float(acc[k]);
+        sums4[3] = float(n_owned);
+        return YB_OK;
+    }
+    int dd_update(int stage, float dt, const float* mean3) override
+    {
+        if (stage == 0) {
+            for (int i = 0; i < n_owned; i++) {
+                for (int k = 0; k < 3; k++) dX[i].v[k] -= mean3[k];
+                X1[i] = X[i] + dX[i] * dt;
+            }
+        } else {
+            for (int i = 0; i < n_owned; i++) {
+                for (int k = 0; k < 3; k++) dX1[i].v[k] -= mean3[k];
+                X[i] += (dX[i] + dX1[i]) * 0.5f * dt;
+                old_v[i].x = (dX[i].v[0] + dX1[i].v[0]) * 0.5f;
+                old_v[i].y = (dX[i].v[1] + dX1[i].v[1]) * 0.5f;
+                old_v[i].z = (dX[i].v[2] + dX1[i].v[2]) * 0.5f;
+            }
+        }
+        return YB_OK;
+    }
+    int dd_read(int which, float* out, int count) override
+    {
+        if (count > capacity) return fail(YB_EINVAL, "n > n_max");
+        if (which == 0)
+            memcpy(out, X.data(), sizeof(Pt<L>) * size_t(count));
+        else if (which == 1)
+            memcpy(out, X1.data(), sizeof(Pt<L>) * size_t(count));
+        else
+            memcpy(out, old_v.data(), sizeof(F3) * size_t(count));
+        return YB_OK;
+    }
+
     int step(float dt) override
     {
+        n_owned = 0;
         if (grows && params.prolif_rate > 0)
             return fail(YB_ENOSYS, "the oracle has no curand: set prolif_rate 0");
         if (n == 0) return YB_OK;
@@ -789,6 +859,24 @@ int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     status = yb_sim_step(sim, dt, n_steps);
     if (status != YB_OK) return status;
     return sim->get_state(h_out, capacity, n_out);
+}
+int yb_dd_load(yb_sim* sim, int stage, const float* X_owned,
+    const float* v_owned, int n_owned, const float* X_ghost,
+    const float* v_ghost, int n_ghost)
+{
+    return sim->dd_load(stage, X_owned, v_owned, n_owned, X_ghost, v_ghost, n_ghost);
+}
+int yb_dd_forces(yb_sim* sim, int stage, float* sums4)
+{
+    return sim->dd_forces(stage, sums4);
+}
+int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3)
+{
+    return sim->dd_update(stage, dt, mean3);
+}
+int yb_dd_read(yb_sim* sim, int which, float* out, int n)
+{
+    return sim->dd_read(which, out, n);
 }
 int yb_sim_profile_sweeps(yb_sim*, int)
 {

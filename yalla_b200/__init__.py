@@ -60,6 +60,15 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_float,
                                         ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_int, _c_int_p]),
+    "yb_dd_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int]),
+    "yb_dd_forces": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p]),
+    "yb_dd_update": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                    ctypes.c_void_p]),
+    "yb_dd_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_int]),
     "yb_sim_profile_sweeps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_sim_read_sweep_profile": (ctypes.c_int, [ctypes.c_void_p, _c_float_p,
                                                  _c_int_p]),
@@ -253,6 +262,25 @@ class Sim:
             self.handle, X_in.ctypes.data, len(X_in), dt, n_steps,
             X_out.ctypes.data, len(X_out), ctypes.byref(n)), "step_host")
         return n.value
+
+    # ---- domain decomposition building blocks (pointers as ints) -----------
+    def dd_load(self, stage, X_owned, v_owned, n_owned, X_ghost, v_ghost,
+                n_ghost):
+        self.lib.check(self.lib.cdll.yb_dd_load(
+            self.handle, stage, X_owned, v_owned, n_owned, X_ghost, v_ghost,
+            n_ghost), "dd_load")
+
+    def dd_forces(self, stage, sums4):
+        self.lib.check(self.lib.cdll.yb_dd_forces(self.handle, stage, sums4),
+                       "dd_forces")
+
+    def dd_update(self, stage, dt, mean3):
+        self.lib.check(self.lib.cdll.yb_dd_update(self.handle, stage, dt, mean3),
+                       "dd_update")
+
+    def dd_read(self, which, out, n):
+        self.lib.check(self.lib.cdll.yb_dd_read(self.handle, which, out, n),
+                       "dd_read")
 
     def profile_sweeps(self, enable=True):
         self.lib.check(self.lib.cdll.yb_sim_profile_sweeps(

@@ -65,6 +65,23 @@ struct yb_sim {
     // Device address of the current cell count (for asynchronous snapshots).
     virtual const int* count_on_device() = 0;
     virtual int current_n() = 0;
+    virtual int dd_load(int, const float*, const float*, int, const float*,
+        const float*, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dd_forces(int, float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dd_update(int, float, const float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dd_read(int, float*, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
     virtual int profile_sweeps(int enable)
     {
         return fail(YB_ENOSYS, "sweep profiling needs the product library");
@@ -136,6 +153,61 @@ struct Sim_base : yb_sim {
         cells.read_sweep_profile(total_ms, launches);
         return YB_OK;
     }
+
+    // ---- domain decomposition (device pointers) ---------------------------
+    int dd_n_owned = 0;
+    int dd_load(int stage, const float* X_owned, const float* v_owned,
+        int n_owned, const float* X_ghost, const float* v_ghost,
+        int n_ghost) override
+    {
+        if (n_owned < 0 || n_ghost < 0 || n_owned + n_ghost > cells.n_max)
+            return fail(YB_EINVAL, "n_owned + n_ghost > n_max");
+        Pt* X = cells.dd_positions(stage);
+        float3* v = cells.dd_velocities();
+        const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+        if (stage == 0) {
+            cudaMemcpyAsync(X, X_owned, sizeof(Pt) * size_t(n_owned), d2d, 0);
+            cudaMemcpyAsync(v, v_owned, sizeof(float3) * size_t(n_owned), d2d, 0);
+            dd_n_owned = n_owned;
+        } else if (n_owned != dd_n_owned) {
+            return fail(YB_EINVAL, "stage 1 must keep the owned cells of stage 0");
+        }
+        if (n_ghost > 0) {
+            cudaMemcpyAsync(X + n_owned, X_ghost, sizeof(Pt) * size_t(n_ghost),
+                d2d, 0);
+            cudaMemcpyAsync(v + n_owned, v_ghost,
+                sizeof(float3) * size_t(n_ghost), d2d, 0);
+        }
+        cells.dd_set_counts(n_owned, n_owned + n_ghost);
+        return check_cuda("yb_dd_load");
+    }
+    int dd_update(int stage, float dt, const float* mean3) override
+    {
+        cells.dd_update(stage, dt, mean3);
+        return check_cuda("yb_dd_update");
+    }
+    int dd_read(int which, float* out, int n) override
+    {
+        if (n > cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+        if (which == 0 || which == 1)
+            cudaMemcpyAsync(out, cells.dd_positions(which),
+                sizeof(Pt) * size_t(n), d2d, 0);
+        else
+            cudaMemcpyAsync(out, cells.dd_velocities(),
+                sizeof(float3) * size_t(n), d2d, 0);
+        return check_cuda("yb_dd_read");
+    }
+    // the sweep needs the model's functor: models that support decomposition
+    // call this from their dd_forces override
+    template<Pairwise_interaction<Pt> force, Pairwise_friction<Pt> friction>
+    int dd_forces_with(int stage, float* sums4)
+    {
+        cells.template dd_forces<force, friction>(stage);
+        cudaMemcpyAsync(sums4, cells.dd_drift_sum(stage), 4 * sizeof(float),
+            cudaMemcpyDeviceToDevice, 0);
+        return check_cuda("yb_dd_forces");
+    }
 #endif
 
     int set_fix(const std::string& name, double value)
@@ -183,6 +255,17 @@ struct Spring_sim : Sim_base<float3, Solver> {
         this->cells.template take_step<force>(dt);
         return 0;
     }
+#ifdef YALLA_B200
+    int dd_forces(int stage, float* sums4) override
+    {
+        // only the grid solver knows ghosts; the Tile solver is replicas-only
+        if constexpr (std::is_same<Solver<float3>, Grid_solver<float3>>::value)
+            return Base::template dd_forces_with<force,
+                friction_w_neighbour<float3>>(stage, sums4);
+        else
+            return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
+    }
+#endif
 };
 
 // ---- float3 + Links: relu_force with link_forces as generic force -----------
@@ -236,6 +319,13 @@ struct Epithelium_sim : Sim_base<Po_cell, Grid_solver> {
         cells.take_step<models::layer_force, friction_on_background>(dt);
         return 0;
     }
+#ifdef YALLA_B200
+    int dd_forces(int stage, float* sums4) override
+    {
+        return dd_forces_with<models::layer_force, friction_on_background<Po_cell>>(
+            stage, sums4);
+    }
+#endif
 };
 
 // Models with a cell type and neighbour counters as Property arrays.
@@ -614,6 +704,28 @@ int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     if (status != YB_OK) return status;
     for (int k = 0; k < n_steps; k++) sim->step(dt);
     return sim->get_state(h_out, capacity, n_out);
+}
+
+int yb_dd_load(yb_sim* sim, int stage, const float* X_owned,
+    const float* v_owned, int n_owned, const float* X_ghost,
+    const float* v_ghost, int n_ghost)
+{
+    return sim->dd_load(stage, X_owned, v_owned, n_owned, X_ghost, v_ghost, n_ghost);
+}
+
+int yb_dd_forces(yb_sim* sim, int stage, float* sums4)
+{
+    return sim->dd_forces(stage, sums4);
+}
+
+int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3)
+{
+    return sim->dd_update(stage, dt, mean3);
+}
+
+int yb_dd_read(yb_sim* sim, int which, float* out, int n)
+{
+    return sim->dd_read(which, out, n);
 }
 
 int yb_sim_profile_sweeps(yb_sim* sim, int enable)
