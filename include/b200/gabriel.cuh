@@ -179,7 +179,7 @@ protected:
         yb::sweep_gabriel<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::GABRIEL_THREADS, 0, s>>>(d_n, this->n_max, this->pos4,
                 this->aux, this->cube_sorted, this->sort.offset, this->cube_size,
-                this->grid_size, this->n_cubes, gabriel_coefficient, d_dX,
+                this->grid_size, this->active_cubes, gabriel_coefficient, d_dX,
                 d_partials, stage, drift_mode, fix_point, d_ctl);
     }
 };

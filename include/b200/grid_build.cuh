@@ -65,9 +65,9 @@ struct Step_ctl {
     int pad0, pad1;
     float drift[2][4];    // per Heun stage: mean (or fixed-point) dX.xyz
     // Domain decomposition (b200/slab.cuh): cells with an id >= n_owned are
-    // ghosts -- neighbours only. 0 means "all cells are owned".
+    // ghosts -- neighbours only; in force while external_drift is set.
     int n_owned;
-    int external_drift;   // 1: the sweep leaves drift[] alone (set by the host)
+    int external_drift;   // 1: decomposed run, the sweep leaves drift[] alone
     int pad2, pad3;
     float drift_sum[2][4];  // per stage: sum of dX.xyz over owned cells, count
 };
@@ -94,13 +94,16 @@ inline Stage_context*& current_stage()
 // cube of a cell within an ulp of a face depends on it.
 // Ids outside [0, n_cubes) trip D_ASSERT in the reference; here they are
 // clamped into the grid and counted.
+// z_half is grid_size / 2 for the reference's cubic grid; a slab of a
+// decomposed domain (b200/slab.cuh) numbers its z layers from its own lower
+// end instead and has n_cubes = grid_size^2 * (its layers).
 __device__ __forceinline__ int cube_of(float x, float y, float z,
-    float cube_size, int grid_size, int n_cubes, int* out_of_grid)
+    float cube_size, int grid_size, int z_half, int n_cubes, int* out_of_grid)
 {
     const long long half = grid_size / 2;
     const long long ix = static_cast<long long>(floorf(x / cube_size)) + half;
     const long long iy = static_cast<long long>(floorf(y / cube_size)) + half;
-    const long long iz = static_cast<long long>(floorf(z / cube_size)) + half;
+    const long long iz = static_cast<long long>(floorf(z / cube_size)) + z_half;
     long long id = ix + iy * grid_size + iz * grid_size * grid_size;
     if (id < 0 || id >= n_cubes) {
         atomicAdd(out_of_grid, 1);
@@ -120,15 +123,15 @@ __device__ __forceinline__ int live_cells(const int* d_n, int n_max)
 template<typename Pt>
 __global__ void __launch_bounds__(256) bin_cells(const int* __restrict__ d_n,
     int n_max, const Pt* __restrict__ d_X, float cube_size, int grid_size,
-    int n_cubes, int* __restrict__ key, int* __restrict__ arrival, int* count,
-    Step_ctl* ctl)
+    int z_half, int n_cubes, int* __restrict__ key, int* __restrict__ arrival,
+    int* count, Step_ctl* ctl)
 {
     const int n = live_cells(d_n, n_max);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += gridDim.x * blockDim.x) {
         const float* p = reinterpret_cast<const float*>(d_X + i);
         const int c = cube_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), cube_size,
-            grid_size, n_cubes, &ctl->out_of_grid);
+            grid_size, z_half, n_cubes, &ctl->out_of_grid);
         key[i] = c;
         arrival[i] = atomicAdd(count + c, 1);
     }

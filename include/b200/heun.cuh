@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) predictor_step(
         store_pt(d_X1, i, X1);
         if (BIN) {
             const int c = cube_of(X1.x, X1.y, X1.z, cube_size, grid_size,
-                n_cubes, &ctl->out_of_grid);
+                grid_size / 2, n_cubes, &ctl->out_of_grid);
             key[i] = c;
             arrival[i] = atomicAdd(count + c, 1);
         }

@@ -247,7 +247,7 @@ __device__ __forceinline__ void finish_drift(float3 my_partial,
     const float3 total = block_sum3<THREADS>(x, y, z, s_red);
     if (threadIdx.x == 0) {
         // with ghosts present only the owned cells count
-        const int owned = ctl->n_owned > 0 && ctl->n_owned < n ? ctl->n_owned : n;
+        const int owned = ctl->external_drift ? min(ctl->n_owned, n) : n;
         ctl->drift_sum[stage][0] = total.x;
         ctl->drift_sum[stage][1] = total.y;
         ctl->drift_sum[stage][2] = total.z;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
     const int n = live_cells(d_n, n_max);
     const int n_chunks = ceil_div(n, SWEEP_THREADS);
     const float reach2 = cube_size * cube_size * SWEEP_PREFILTER_SLACK;
-    const int n_owned = ctl->n_owned > 0 ? ctl->n_owned : n_max;
+    const int n_owned = ctl->external_drift ? ctl->n_owned : n_max;
 
     if (t == 0) mbar_init(&s_bar, 1);
     __syncthreads();

@@ -24,6 +24,7 @@
 
 #include <assert.h>
 #include <stdlib.h>
+#include <cmath>
 // The solver itself does not use Thrust. These four headers are included only
 // because ya||a models call thrust::fill / thrust::reduce in their own code and
 // rely on solvers.cuh to have pulled them in (reference: solvers.cuh:5-8).
@@ -43,6 +44,7 @@
 #include "b200/heun.cuh"
 #include "b200/layout.cuh"
 #include "b200/pair_sweep.cuh"
+#include "b200/slab.cuh"
 
 #define YALLA_B200 1
 
@@ -247,6 +249,7 @@ public:
     {
         cudaStreamSynchronize(stream);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        if (slab.capacity > 0) slab.release();
         cudaFreeHost(h_n_pinned);
         cudaStreamDestroy(capture_stream);
         cudaFree(d_partials);
@@ -333,6 +336,98 @@ public:
             yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
         YB_CUDA(cudaGetLastError());
+    }
+
+    // ---- Extension: slab decomposition without host round trips ---------------
+    // The same building blocks, but packing/unpacking of halo cells and of
+    // migrating cells happens in kernels (b200/slab.cuh) and all counts stay on
+    // the device: between slab_begin and the end of the run the host never has
+    // to wait for the GPU. Exchange buffers hold a 4-float header (header[0] =
+    // bits of the record count) followed by `capacity` records of
+    // sizeof(Pt) / 4 + 3 floats; the caller ships them to the neighbouring
+    // ranks at full size (NCCL send/recv, yalla_b200/dd.py).
+    void slab_begin(float z_lo, float z_hi, float halo, int capacity)
+    {
+        if (slab.capacity == 0) slab.allocate(n_max);
+        slab.capacity = capacity;
+        slab.z_lo = z_lo, slab.z_hi = z_hi, slab.halo = halo;
+        slab.has_lower = std::isfinite(z_lo), slab.has_upper = std::isfinite(z_hi);
+        dd_set_counts(0, 0);
+    }
+    void slab_set_owned(const Pt* d_X_new, const float3* d_v_new, int n_owned)
+    {
+        assert(n_owned <= n_max);
+        YB_CUDA(cudaMemcpyAsync(d_X, d_X_new, sizeof(Pt) * size_t(n_owned),
+            cudaMemcpyDeviceToDevice, stream));
+        YB_CUDA(cudaMemcpyAsync(d_old_v, d_v_new, sizeof(float3) * size_t(n_owned),
+            cudaMemcpyDeviceToDevice, stream));
+        dd_set_counts(n_owned, n_owned);
+    }
+    // what = 0 / 1: the halo of the stage's positions (X / X1); 2: the cells that
+    // left the slab during the step.
+    void slab_pack(int what, float* send_lo, float* send_hi)
+    {
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        const bool migration = what == 2;
+        const Pt* P = what == 1 ? d_X1 : d_X;
+        const float lo_edge = migration ? slab.z_lo : slab.z_lo + slab.halo;
+        const float hi_edge = migration ? slab.z_hi : slab.z_hi - slab.halo;
+        yb::slab_flags<Pt><<<blocks, 256, 0, stream>>>(d_ctl, P, lo_edge, hi_edge,
+            slab.has_lower, slab.has_upper, slab.flag[0], slab.flag[1],
+            migration ? slab.flag[2] : nullptr);
+        for (int k = 0; k < (migration ? 3 : 2); k++)
+            yb::scan_bins<<<slab.n_tiles, yb::SCAN_THREADS, 0, stream>>>(
+                slab.flag[k], slab.off[k], slab.n_tiles, slab.status,
+                slab.scan_ctl);
+        yb::slab_pack<Pt><<<blocks, 256, 0, stream>>>(d_ctl, P, d_old_v,
+            slab.off[0], slab.off[1], send_lo, send_hi, slab.capacity);
+        if (migration)  // X1 and dX are free at the end of a step: scratch
+            yb::slab_compact_stayers<Pt><<<blocks, 256, 0, stream>>>(d_ctl, d_X,
+                d_old_v, slab.off[2], d_X1, reinterpret_cast<float3*>(d_dX));
+        YB_CUDA(cudaGetLastError());
+    }
+    void slab_unpack(int what, const float* recv_lo, const float* recv_hi)
+    {
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        if (what == 2) {
+            yb::slab_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, slab.off[2],
+                d_X1, reinterpret_cast<const float3*>(d_dX), recv_lo, recv_hi,
+                slab.has_lower, slab.has_upper, n_max, d_X, d_old_v,
+                slab.new_count);
+            yb::slab_commit_count<<<1, 1, 0, stream>>>(
+                d_ctl, slab.new_count, d_n);
+        } else {
+            yb::slab_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(d_ctl,
+                what == 1 ? d_X1 : d_X, d_old_v, recv_lo, recv_hi,
+                slab.has_lower, slab.has_upper, n_max, d_n);
+        }
+        YB_CUDA(cudaGetLastError());
+    }
+    // Predictor / corrector with drift = (sums over all slabs) / (count over all
+    // slabs); d_sums4 = {sum dX.x, .y, .z, n} after the caller's all-reduce.
+    void slab_update(int stage, float dt, const float* d_sums4)
+    {
+        yb::slab_set_drift<<<1, 1, 0, stream>>>(d_ctl, stage, d_sums4);
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        if (stage == 0)
+            yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+        else
+            yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
+                d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+        YB_CUDA(cudaGetLastError());
+    }
+    // Blocking: owned cells, owned + ghost cells, and the number of problems seen
+    // (cells outside the grid; exchange-buffer overflows count 2^20 each).
+    void slab_counts(int* n_owned, int* n_total, int* problems)
+    {
+        yb::Step_ctl snapshot;
+        YB_CUDA(cudaMemcpyAsync(&snapshot, d_ctl, sizeof(snapshot),
+            cudaMemcpyDeviceToHost, stream));
+        const int total = get_d_n();
+        if (n_owned) *n_owned = snapshot.n_owned;
+        if (n_total) *n_total = total;
+        if (problems) *problems = snapshot.out_of_grid;
     }
 
     // Extension: time the pairwise sweep kernels with CUDA events on the
@@ -447,6 +542,7 @@ private:
     cudaStream_t capture_stream;
     std::vector<yb::Step_graph> graphs;
     int* h_n_pinned = nullptr;
+    yb::Slab_scratch slab;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
 
@@ -656,8 +752,8 @@ public:
         if (n > 0) {
             const int blocks = yb::stride_grid(n, 256, sms);
             yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n_scratch, n_max, d_X,
-                cube_size, grid_size, n_cubes, sort.key, sort.arrival,
-                sort.count, d_ctl);
+                cube_size, grid_size, grid_size / 2, n_cubes, sort.key,
+                sort.arrival, sort.count, d_ctl);
             yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
                 sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
             yb::place_ids<<<blocks, 256, 0, s>>>(d_n_scratch, n_max, sort.key,
@@ -691,7 +787,8 @@ public:
 
     Grid_computer(int n_max, int grid_size = 50, float cube_size = 1)
         : cube_size{cube_size}, n_max{n_max}, grid_size{grid_size},
-          n_cubes{grid_size * grid_size * grid_size}
+          n_cubes{grid_size * grid_size * grid_size}, z_half{grid_size / 2},
+          active_cubes{grid_size * grid_size * grid_size}
     {
         yb::upload_nhood(grid_size);
         sort.allocate(n_max, n_cubes);
@@ -744,9 +841,11 @@ protected:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (!binned_by_predictor)
             yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, cube_size,
-                grid_size, n_cubes, sort.key, sort.arrival, sort.count, d_ctl);
-        yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
-            sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
+                grid_size, z_half, active_cubes, sort.key, sort.arrival,
+                sort.count, d_ctl);
+        const int tiles = yb::ceil_div(active_cubes + 1, yb::SCAN_TILE);
+        yb::scan_bins<<<tiles, yb::SCAN_THREADS, 0, s>>>(
+            sort.count, sort.offset, tiles, sort.status, d_ctl);
         yb::place_ids<<<blocks, 256, 0, s>>>(
             d_n, n_max, sort.key, sort.arrival, sort.offset, sort.slot_id);
         yb::reorder_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, d_old_v,
@@ -775,7 +874,7 @@ protected:
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::SWEEP_THREADS, yb::SWEEP_SMEM, s>>>(d_n, n_max, pos4,
-                aux, cube_sorted, sort.offset, cube_size, grid_size, n_cubes,
+                aux, cube_sorted, sort.offset, cube_size, grid_size, active_cubes,
                 d_dX, d_partials, stage, drift_mode, fix_point, d_ctl);
     }
 
@@ -792,6 +891,20 @@ protected:
     float4* aux;
     int* cube_sorted;
     const int n_max, grid_size, n_cubes;
+    // z numbering of the grid: the reference's cubic grid by default; a slab of
+    // a decomposed domain uses only its own layers (dd_slab_grid below)
+    int z_half, active_cubes;
+
+public:
+    // Extension (domain decomposition): restrict the grid to the z layers
+    // [first_layer, first_layer + n_layers) of the global cubic grid. Keeps the
+    // per-cube tables (and the scan over them) proportional to the slab.
+    void dd_slab_grid(int first_layer, int n_layers)
+    {
+        assert(n_layers >= 1 && n_layers <= grid_size);
+        z_half = grid_size / 2 - first_layer;
+        active_cubes = grid_size * grid_size * n_layers;
+    }
 };
 
 template<typename Pt>

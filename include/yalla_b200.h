@@ -140,6 +140,31 @@ int yb_dd_forces(yb_sim* sim, int stage, float* sums4);
 int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3);
 int yb_dd_read(yb_sim* sim, int which, float* out, int n);
 
+/* Slab decomposition without host round trips: packing/unpacking of halo and
+ * migrating cells happens inside the library and all counts stay in its memory
+ * space. Exchange buffers hold 4 header floats (header[0] = bits of the record
+ * count) followed by `capacity` records of lanes + 3 floats (cell, old
+ * velocity); the caller ships whole buffers to the neighbouring ranks.
+ *
+ * yb_slab_begin   this solver owns z_lo <= z < z_hi (+-INFINITY at the ends);
+ *                 halo = width of the strip sent to a neighbour; the grid is
+ *                 restricted to n_layers z layers starting at first_layer of
+ *                 the cubic grid (n_layers <= 0: keep the whole grid).
+ * yb_slab_pack    what 0 / 1: halo of X / X1 -> send_lo, send_hi;
+ *                 what 2: cells that left the slab (and compaction of the rest)
+ * yb_slab_unpack  what 0 / 1: append received ghosts; 2: append arrivals
+ * yb_slab_update  predictor / corrector, drift = sums4[0..2] / sums4[3] with
+ *                 sums4 already reduced over all slabs
+ * yb_slab_counts  blocking diagnostics: owned, owned + ghosts, problems */
+int yb_slab_begin(yb_sim* sim, float z_lo, float z_hi, float halo,
+    int capacity, int first_layer, int n_layers);
+int yb_slab_set_owned(yb_sim* sim, const float* X, const float* v, int n_owned);
+int yb_slab_pack(yb_sim* sim, int what, float* send_lo, float* send_hi);
+int yb_slab_unpack(yb_sim* sim, int what, const float* recv_lo,
+    const float* recv_hi);
+int yb_slab_update(yb_sim* sim, int stage, float dt, const float* sums4);
+int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems);
+
 /* Current cell count (blocking read of d_n: Solution::get_d_n). */
 int yb_sim_n(yb_sim* sim, int* n_out);
 int yb_sim_sync(yb_sim* sim);

@@ -407,6 +407,12 @@ struct yb_sim {
     virtual int dd_forces(int, float*) = 0;
     virtual int dd_update(int, float, const float*) = 0;
     virtual int dd_read(int, float*, int) = 0;
+    virtual int slab_begin(float, float, float, int) = 0;
+    virtual int slab_set_owned(const float*, const float*, int) = 0;
+    virtual int slab_pack(int, float*, float*) = 0;
+    virtual int slab_unpack(int, const float*, const float*) = 0;
+    virtual int slab_update(int, float, const float*) = 0;
+    virtual int slab_counts(int*, int*, int*) = 0;
 };
 
 namespace {
@@ -428,6 +434,10 @@ struct Sim : yb_sim {
     bool fix_com = true, fix_com_z = false;
     int fix_point = 0;
     int n_owned = 0;  // domain decomposition: cells >= n_owned are ghosts
+    float slab_z_lo = 0, slab_z_hi = 0, slab_halo = 0;
+    int slab_capacity = 0;
+    bool has_lower = false, has_upper = false;
+    std::vector<int> stayers;
 
     Sim(int n_max, Solver solver, Force<L> force, Friction friction,
         int grid_size, float cube_size)
@@ -687,6 +697,107 @@ struct Sim : yb_sim {
         return YB_OK;
     }
 
+    // ---- slab API: same semantics as the device kernels in b200/slab.cuh,
+    //      written as plain index-order loops -----------------------------------
+    static int header_count(const float* buffer)
+    {
+        int count;
+        memcpy(&count, buffer, sizeof(int));
+        return count;
+    }
+    static void set_header(float* buffer, int count)
+    {
+        memcpy(buffer, &count, sizeof(int));
+    }
+    void put_record(float* record, const std::vector<Pt<L>>& P, int i) const
+    {
+        memcpy(record, P[i].v, sizeof(float) * L);
+        record[L + 0] = old_v[i].x;
+        record[L + 1] = old_v[i].y;
+        record[L + 2] = old_v[i].z;
+    }
+    void get_record(const float* record, std::vector<Pt<L>>& P, int i)
+    {
+        memcpy(P[i].v, record, sizeof(float) * L);
+        old_v[i] = F3{record[L + 0], record[L + 1], record[L + 2]};
+    }
+    int slab_begin(float z_lo, float z_hi, float halo, int cap) override
+    {
+        if (solver != GRID || counts_neighbours || has_links)
+            return fail(YB_ENOSYS, "domain decomposition needs a plain Grid model");
+        slab_z_lo = z_lo, slab_z_hi = z_hi, slab_halo = halo, slab_capacity = cap;
+        has_lower = std::isfinite(z_lo), has_upper = std::isfinite(z_hi);
+        n_owned = n = 0;
+        return YB_OK;
+    }
+    int slab_set_owned(const float* X_new, const float* v_new, int owned) override
+    {
+        if (owned > capacity) return fail(YB_EINVAL, "n_owned > n_max");
+        memcpy(X.data(), X_new, sizeof(Pt<L>) * size_t(owned));
+        memcpy(old_v.data(), v_new, sizeof(F3) * size_t(owned));
+        n_owned = n = owned;
+        return YB_OK;
+    }
+    int slab_pack(int what, float* send_lo, float* send_hi) override
+    {
+        const bool migration = what == 2;
+        const std::vector<Pt<L>>& P = what == 1 ? X1 : X;
+        const float lo_edge = migration ? slab_z_lo : slab_z_lo + slab_halo;
+        const float hi_edge = migration ? slab_z_hi : slab_z_hi - slab_halo;
+        const int W = L + 3;
+        int n_lo = 0, n_hi = 0;
+        stayers.clear();
+        for (int i = 0; i < n_owned; i++) {
+            const float z = P[i].v[2];
+            const bool lo = has_lower && z < lo_edge;
+            const bool hi = has_upper && z >= hi_edge;
+            if (lo && n_lo < slab_capacity)
+                put_record(send_lo + 4 + size_t(n_lo++) * W, P, i);
+            if (hi && n_hi < slab_capacity)
+                put_record(send_hi + 4 + size_t(n_hi++) * W, P, i);
+            if (migration && !(lo || hi)) stayers.push_back(i);
+        }
+        set_header(send_lo, n_lo);
+        set_header(send_hi, n_hi);
+        return YB_OK;
+    }
+    int slab_unpack(int what, const float* recv_lo, const float* recv_hi) override
+    {
+        const int W = L + 3;
+        const int n_lo = has_lower ? header_count(recv_lo) : 0;
+        const int n_hi = has_upper ? header_count(recv_hi) : 0;
+        int base = n_owned;
+        std::vector<Pt<L>>& P = what == 1 ? X1 : X;
+        if (what == 2) {
+            for (size_t k = 0; k < stayers.size(); k++) {  // stable, in place
+                X[k] = X[stayers[k]];
+                old_v[k] = old_v[stayers[k]];
+            }
+            base = int(stayers.size());
+        }
+        if (base + n_lo + n_hi > capacity) return fail(YB_EINVAL, "n > n_max");
+        for (int r = 0; r < n_lo; r++)
+            get_record(recv_lo + 4 + size_t(r) * W, P, base + r);
+        for (int r = 0; r < n_hi; r++)
+            get_record(recv_hi + 4 + size_t(r) * W, P, base + n_lo + r);
+        n = base + n_lo + n_hi;
+        if (what == 2) n_owned = n;
+        return YB_OK;
+    }
+    int slab_update(int stage, float dt, const float* sums4) override
+    {
+        const float inv_n = static_cast<float>(1. / sums4[3]);
+        const float mean[3] = {sums4[0] * inv_n, sums4[1] * inv_n, sums4[2] * inv_n};
+        return dd_update(stage, dt, mean);
+    }
+    int slab_counts(int* owned, int* total, int* problems) override
+    {
+        if (owned) *owned = n_owned;
+        if (total) *total = n;
+        if (problems) *problems = 0;
+        return YB_OK;
+    }
+
     int step(float dt) override
     {
         n_owned = 0;
@@ -877,6 +988,32 @@ int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3)
 int yb_dd_read(yb_sim* sim, int which, float* out, int n)
 {
     return sim->dd_read(which, out, n);
+}
+int yb_slab_begin(yb_sim* sim, float z_lo, float z_hi, float halo,
+    int capacity, int, int)
+{
+    return sim->slab_begin(z_lo, z_hi, halo, capacity);
+}
+int yb_slab_set_owned(yb_sim* sim, const float* X, const float* v, int n_owned)
+{
+    return sim->slab_set_owned(X, v, n_owned);
+}
+int yb_slab_pack(yb_sim* sim, int what, float* send_lo, float* send_hi)
+{
+    return sim->slab_pack(what, send_lo, send_hi);
+}
+int yb_slab_unpack(yb_sim* sim, int what, const float* recv_lo,
+    const float* recv_hi)
+{
+    return sim->slab_unpack(what, recv_lo, recv_hi);
+}
+int yb_slab_update(yb_sim* sim, int stage, float dt, const float* sums4)
+{
+    return sim->slab_update(stage, dt, sums4);
+}
+int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems)
+{
+    return sim->slab_counts(n_owned, n_total, problems);
 }
 int yb_sim_profile_sweeps(yb_sim*, int)
 {

@@ -69,6 +69,19 @@ SIGNATURES = {
                                     ctypes.c_void_p]),
     "yb_dd_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                   ctypes.c_int]),
+    "yb_slab_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int]),
+    "yb_slab_set_owned": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_int]),
+    "yb_slab_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
+    "yb_slab_unpack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_slab_update": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_float, ctypes.c_void_p]),
+    "yb_slab_counts": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_int_p,
+                                      _c_int_p]),
     "yb_sim_profile_sweeps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_sim_read_sweep_profile": (ctypes.c_int, [ctypes.c_void_p, _c_float_p,
                                                  _c_int_p]),
@@ -281,6 +294,35 @@ class Sim:
     def dd_read(self, which, out, n):
         self.lib.check(self.lib.cdll.yb_dd_read(self.handle, which, out, n),
                        "dd_read")
+
+    def slab_begin(self, z_lo, z_hi, halo, capacity, first_layer=0, n_layers=0):
+        self.lib.check(self.lib.cdll.yb_slab_begin(
+            self.handle, z_lo, z_hi, halo, capacity, first_layer, n_layers),
+            "slab_begin")
+
+    def slab_set_owned(self, X, v, n_owned):
+        self.lib.check(self.lib.cdll.yb_slab_set_owned(self.handle, X, v, n_owned),
+                       "slab_set_owned")
+
+    def slab_pack(self, what, send_lo, send_hi):
+        self.lib.check(self.lib.cdll.yb_slab_pack(self.handle, what, send_lo,
+                                                  send_hi), "slab_pack")
+
+    def slab_unpack(self, what, recv_lo, recv_hi):
+        self.lib.check(self.lib.cdll.yb_slab_unpack(self.handle, what, recv_lo,
+                                                    recv_hi), "slab_unpack")
+
+    def slab_update(self, stage, dt, sums4):
+        self.lib.check(self.lib.cdll.yb_slab_update(self.handle, stage, dt, sums4),
+                       "slab_update")
+
+    def slab_counts(self):
+        """-> (owned cells, owned + ghost cells, problems); blocks"""
+        owned, total, problems = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_slab_counts(
+            self.handle, ctypes.byref(owned), ctypes.byref(total),
+            ctypes.byref(problems)), "slab_counts")
+        return owned.value, total.value, problems.value
 
     def profile_sweeps(self, enable=True):
         self.lib.check(self.lib.cdll.yb_sim_profile_sweeps(

@@ -82,6 +82,30 @@ struct yb_sim {
     {
         return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
     }
+    virtual int slab_begin(float, float, float, int, int, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int slab_set_owned(const float*, const float*, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int slab_pack(int, float*, float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int slab_unpack(int, const float*, const float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int slab_update(int, float, const float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int slab_counts(int*, int*, int*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
     virtual int profile_sweeps(int enable)
     {
         return fail(YB_ENOSYS, "sweep profiling needs the product library");
@@ -197,6 +221,52 @@ struct Sim_base : yb_sim {
             cudaMemcpyAsync(out, cells.dd_velocities(),
                 sizeof(float3) * size_t(n), d2d, 0);
         return check_cuda("yb_dd_read");
+    }
+    int slab_begin(float z_lo, float z_hi, float halo, int capacity,
+        int first_layer, int n_layers) override
+    {
+        return slab_begin_impl(z_lo, z_hi, halo, capacity, first_layer, n_layers,
+            std::is_same<Solver<Pt>, Grid_solver<Pt>>{});
+    }
+    int slab_begin_impl(float z_lo, float z_hi, float halo, int capacity,
+        int first_layer, int n_layers, std::true_type)
+    {
+        if (capacity <= 0) return fail(YB_EINVAL, "capacity must be positive");
+        if (n_layers > 0) cells.dd_slab_grid(first_layer, n_layers);
+        cells.slab_begin(z_lo, z_hi, halo, capacity);
+        return check_cuda("yb_slab_begin");
+    }
+    int slab_begin_impl(float, float, float, int, int, int, std::false_type)
+    {
+        return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
+    }
+    int slab_set_owned(const float* X, const float* v, int n_owned) override
+    {
+        if (n_owned < 0 || n_owned > cells.n_max)
+            return fail(YB_EINVAL, "n_owned > n_max");
+        cells.slab_set_owned(reinterpret_cast<const Pt*>(X),
+            reinterpret_cast<const float3*>(v), n_owned);
+        return check_cuda("yb_slab_set_owned");
+    }
+    int slab_pack(int what, float* send_lo, float* send_hi) override
+    {
+        cells.slab_pack(what, send_lo, send_hi);
+        return check_cuda("yb_slab_pack");
+    }
+    int slab_unpack(int what, const float* recv_lo, const float* recv_hi) override
+    {
+        cells.slab_unpack(what, recv_lo, recv_hi);
+        return check_cuda("yb_slab_unpack");
+    }
+    int slab_update(int stage, float dt, const float* sums4) override
+    {
+        cells.slab_update(stage, dt, sums4);
+        return check_cuda("yb_slab_update");
+    }
+    int slab_counts(int* n_owned, int* n_total, int* problems) override
+    {
+        cells.slab_counts(n_owned, n_total, problems);
+        return check_cuda("yb_slab_counts");
     }
     // the sweep needs the model's functor: models that support decomposition
     // call this from their dd_forces override
@@ -726,6 +796,38 @@ int yb_dd_update(yb_sim* sim, int stage, float dt, const float* mean3)
 int yb_dd_read(yb_sim* sim, int which, float* out, int n)
 {
     return sim->dd_read(which, out, n);
+}
+
+int yb_slab_begin(yb_sim* sim, float z_lo, float z_hi, float halo,
+    int capacity, int first_layer, int n_layers)
+{
+    return sim->slab_begin(z_lo, z_hi, halo, capacity, first_layer, n_layers);
+}
+
+int yb_slab_set_owned(yb_sim* sim, const float* X, const float* v, int n_owned)
+{
+    return sim->slab_set_owned(X, v, n_owned);
+}
+
+int yb_slab_pack(yb_sim* sim, int what, float* send_lo, float* send_hi)
+{
+    return sim->slab_pack(what, send_lo, send_hi);
+}
+
+int yb_slab_unpack(yb_sim* sim, int what, const float* recv_lo,
+    const float* recv_hi)
+{
+    return sim->slab_unpack(what, recv_lo, recv_hi);
+}
+
+int yb_slab_update(yb_sim* sim, int stage, float dt, const float* sums4)
+{
+    return sim->slab_update(stage, dt, sums4);
+}
+
+int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems)
+{
+    return sim->slab_counts(n_owned, n_total, problems);
 }
 
 int yb_sim_profile_sweeps(yb_sim* sim, int enable)

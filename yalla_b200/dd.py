@@ -7,15 +7,19 @@ solver through the ``yb_dd_*`` building blocks of include/yalla_b200.h. Because
 interactions are strictly shorter than cube_size, a slab needs a halo of one
 cube from each neighbour; per Heun stage:
 
-    pack boundary cells -> exchange with the two neighbours (send/recv)
-    -> yb_dd_load (owned + ghosts) -> yb_dd_forces (grid build + sweep)
+    yb_slab_pack (boundary cells -> exchange buffers, on the device)
+    -> send/recv whole buffers with the two neighbours
+    -> yb_slab_unpack (ghosts behind the owned cells)
+    -> yb_dd_forces (grid build + sweep; ghosts are partners only)
     -> all-reduce {sum dX, n} (the drift is the GLOBAL mean force,
-       solvers.cuh:241-255) -> yb_dd_update (predictor / corrector)
+       solvers.cuh:241-255) -> yb_slab_update (predictor / corrector)
 
-and once per step cells that crossed a cut migrate to the neighbour. torch is
-used for the plumbing only (masks, gathers, send/recv, all-reduce); grid build,
-sweep and updates are the library's kernels. The module is device-agnostic: with
-the CPU oracle and gloo the very same code runs in the CPU test-suite.
+and once per step cells that crossed a cut migrate to the neighbour the same
+way. torch is used for the plumbing only (buffers, send/recv, all-reduce);
+packing, grid build, sweep and updates are the library's kernels, and because
+all counts stay on the device a step never synchronises with the host. The
+module is device-agnostic: with the CPU oracle and gloo the very same code runs
+in the CPU test-suite.
 
 Limits (documented in DESIGN.md): Grid models without per-id property arrays
 ("relu_grid", "spring_grid", "epithelium"); cell identity is not tracked across
@@ -68,13 +72,21 @@ def lattice_ball_slab(radius, dist_to_nb, z_lo, z_hi, rng, jitter=0.05):
 
 
 class SlabDomain:
-    """One rank's slab: owns the cells with z_lo <= z < z_hi."""
+    """One rank's slab: owns the cells with z_lo <= z < z_hi.
+
+    State and all cell counts live inside the library; a step posts kernels,
+    fixed-size neighbour exchanges and two 16-byte all-reduces and never waits
+    for the device. `n_owned`, `counts()` and `gather_all()` do block and are
+    meant for set-up, diagnostics and tests.
+    """
 
     def __init__(self, lib, model, n_max, grid_size, cube_size, z_lo, z_hi,
-                 device, halo=1.5, group=None):
+                 device, halo=1.5, halo_capacity=None, group=None,
+                 local_grid=True):
         self.lib = lib
         self.sim = lib.sim(model, n_max, grid_size, cube_size)
         self.lanes = self.sim.lanes
+        self.width = self.lanes + 3  # floats per exchanged record
         self.n_max = n_max
         self.cube_size = float(cube_size)
         self.z_lo, self.z_hi = float(z_lo), float(z_hi)
@@ -85,10 +97,26 @@ class SlabDomain:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.lower = self.rank - 1 if self.rank > 0 else None
         self.upper = self.rank + 1 if self.rank < self.world - 1 else None
-        self.X = torch.zeros((0, self.lanes), dtype=torch.float32, device=self.device)
-        self.v = torch.zeros((0, 3), dtype=torch.float32, device=self.device)
+        self.capacity = int(halo_capacity or max(1024, n_max // 4))
+        size = 4 + self.capacity * self.width
+        self.send = [torch.zeros(size, dtype=torch.float32, device=self.device)
+                     for _ in range(2)]
+        self.recv = [torch.zeros(size, dtype=torch.float32, device=self.device)
+                     for _ in range(2)]
         self.sums = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self.stats = {"ghosts": 0, "migrated": 0}
+        # the solver's grid only needs the z layers this slab can touch: its own
+        # range plus the halo and one cube of slack for cells on the move
+        first_layer, n_layers = 0, 0
+        if local_grid and self.world > 1:
+            half = grid_size // 2
+            lo = -half if not np.isfinite(z_lo) else int(
+                np.floor((z_lo - self.halo) / cube_size)) - 2
+            hi = half if not np.isfinite(z_hi) else int(
+                np.ceil((z_hi + self.halo) / cube_size)) + 2
+            lo, hi = max(lo, -half), min(hi, half)
+            first_layer, n_layers = lo + half, hi - lo
+        self.sim.slab_begin(self.z_lo, self.z_hi, self.halo, self.capacity,
+                            first_layer, n_layers)
 
     def close(self):
         self.sim.close()
@@ -96,16 +124,25 @@ class SlabDomain:
     # ---- state ---------------------------------------------------------------
     def set_cells(self, X, v=None):
         X = torch.as_tensor(X, dtype=torch.float32).reshape(-1, self.lanes)
-        self.X = X.to(self.device).contiguous()
+        X = X.to(self.device).contiguous()
         if v is None:
-            self.v = torch.zeros((len(self.X), 3), dtype=torch.float32,
-                                 device=self.device)
+            v = torch.zeros((len(X), 3), dtype=torch.float32, device=self.device)
         else:
-            self.v = torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous()
+            v = torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous()
+        self.sim.slab_set_owned(X.data_ptr(), v.data_ptr(), len(X))
+        self._sync()
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def counts(self):
+        """(owned, owned + ghosts, problems) -- blocks."""
+        return self.sim.slab_counts()
 
     @property
     def n_owned(self):
-        return int(self.X.shape[0])
+        return self.counts()[0]
 
     def total_cells(self):
         count = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
@@ -113,113 +150,58 @@ class SlabDomain:
             dist.all_reduce(count, group=self.group)
         return int(count.item())
 
+    def owned_state(self):
+        """(X, v) of the owned cells as new tensors -- blocks."""
+        n = self.n_owned
+        X = torch.empty((n, self.lanes), dtype=torch.float32, device=self.device)
+        v = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        self.sim.dd_read(0, X.data_ptr(), n)
+        self.sim.dd_read(2, v.data_ptr(), n)
+        self._sync()
+        return X, v
+
     # ---- neighbour exchange ------------------------------------------------------
-    def _exchange(self, to_lower, to_upper):
-        """Send one [m, width] tensor to each existing neighbour, receive
-        theirs; returns (from_lower, from_upper), empty where there is none."""
-        width = to_lower.shape[1]
-        empty = torch.zeros((0, width), dtype=torch.float32, device=self.device)
-        if self.world == 1:
-            return empty, empty
-        counts = torch.tensor([to_lower.shape[0], to_upper.shape[0]],
-                              dtype=torch.int64, device=self.device)
-        gathered = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(gathered, counts, group=self.group)
-        gathered = gathered.view(self.world, 2).tolist()
-        from_lower, from_upper = empty, empty
+    def _exchange(self):
+        """Ship send[0] to the lower and send[1] to the upper neighbour, receive
+        their buffers into recv[0] / recv[1]. Whole buffers: no counts needed."""
         ops = []
         if self.lower is not None:
-            incoming = int(gathered[self.lower][1])  # what it sends upwards
-            from_lower = torch.empty((incoming, width), dtype=torch.float32,
-                                     device=self.device)
-            if to_lower.shape[0] > 0:
-                ops.append(dist.P2POp(dist.isend, to_lower.contiguous(), self.lower,
-                                      self.group))
-            if incoming > 0:
-                ops.append(dist.P2POp(dist.irecv, from_lower, self.lower, self.group))
+            ops.append(dist.P2POp(dist.isend, self.send[0], self.lower, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv[0], self.lower, self.group))
         if self.upper is not None:
-            incoming = int(gathered[self.upper][0])  # what it sends downwards
-            from_upper = torch.empty((incoming, width), dtype=torch.float32,
-                                     device=self.device)
-            if to_upper.shape[0] > 0:
-                ops.append(dist.P2POp(dist.isend, to_upper.contiguous(), self.upper,
-                                      self.group))
-            if incoming > 0:
-                ops.append(dist.P2POp(dist.irecv, from_upper, self.upper, self.group))
+            ops.append(dist.P2POp(dist.isend, self.send[1], self.upper, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv[1], self.upper, self.group))
         if ops:
             for work in dist.batch_isend_irecv(ops):
                 work.wait()
-        return from_lower, from_upper
 
-    def _halo(self, X):
-        """Ghost cells for the positions X of the owned cells: the neighbours'
-        cells within `halo` of the shared cut (positions and old velocities)."""
-        payload = torch.cat([X, self.v], dim=1)
-        z = X[:, 2]
-        none = payload[:0]
-        to_lower = payload[z < self.z_lo + self.halo] if self.lower is not None else none
-        to_upper = payload[z >= self.z_hi - self.halo] if self.upper is not None else none
-        from_lower, from_upper = self._exchange(to_lower, to_upper)
-        ghosts = torch.cat([from_lower, from_upper], dim=0)
-        return ghosts[:, :self.lanes].contiguous(), ghosts[:, self.lanes:].contiguous()
+    def _round(self, what):
+        self.sim.slab_pack(what, self.send[0].data_ptr(), self.send[1].data_ptr())
+        self._exchange()
+        self.sim.slab_unpack(what, self.recv[0].data_ptr(), self.recv[1].data_ptr())
 
     # ---- one Heun step ---------------------------------------------------------------
-    def _stage(self, stage, X_stage, dt):
-        gX, gv = self._halo(X_stage)
-        n, n_ghost = self.n_owned, int(gX.shape[0])
-        if n + n_ghost > self.n_max:
-            raise RuntimeError(f"rank {self.rank}: {n} owned + {n_ghost} ghost "
-                               f"cells exceed n_max = {self.n_max}")
-        self.stats["ghosts"] = n_ghost
-        if stage == 0:
-            self.sim.dd_load(0, self.X.data_ptr(), self.v.data_ptr(), n,
-                             gX.data_ptr(), gv.data_ptr(), n_ghost)
-        else:
-            self.sim.dd_load(1, 0, 0, n, gX.data_ptr(), gv.data_ptr(), n_ghost)
-        self.sim.dd_forces(stage, self.sums.data_ptr())
-        if self.world > 1:
-            dist.all_reduce(self.sums, group=self.group)
-        mean = (self.sums[:3] / self.sums[3]).contiguous()
-        self.sim.dd_update(stage, dt, mean.data_ptr())
-        # gX, gv and mean must outlive the asynchronous copies that read them
-        self._keep = (gX, gv, mean)
-
     def step(self, dt):
-        n = self.n_owned
-        self._stage(0, self.X, dt)
-        X1 = torch.empty_like(self.X)
-        self.sim.dd_read(1, X1.data_ptr(), n)
-        self._stage(1, X1, dt)
-        self.sim.dd_read(0, self.X.data_ptr(), n)
-        self.sim.dd_read(2, self.v.data_ptr(), n)
-        self._migrate()
-
-    def _migrate(self):
-        """Hand cells that crossed a cut to the neighbouring slab."""
-        if self.world == 1:
-            return
-        payload = torch.cat([self.X, self.v], dim=1)
-        z = self.X[:, 2]
-        down = (z < self.z_lo) if self.lower is not None else torch.zeros_like(z, dtype=torch.bool)
-        up = (z >= self.z_hi) if self.upper is not None else torch.zeros_like(z, dtype=torch.bool)
-        from_lower, from_upper = self._exchange(payload[down], payload[up])
-        stay = payload[~(down | up)]
-        merged = torch.cat([stay, from_lower, from_upper], dim=0)
-        self.stats["migrated"] = int(down.sum().item() + up.sum().item())
-        self.X = merged[:, :self.lanes].contiguous()
-        self.v = merged[:, self.lanes:].contiguous()
+        for stage in (0, 1):
+            self._round(stage)  # halo of X resp. X1
+            self.sim.dd_forces(stage, self.sums.data_ptr())
+            if self.world > 1:
+                dist.all_reduce(self.sums, group=self.group)
+            self.sim.slab_update(stage, dt, self.sums.data_ptr())
+        self._round(2)  # migration
 
     def gather_all(self):
         """All cells of the tissue on every rank (tests and small runs only)."""
+        X, _ = self.owned_state()
         if self.world == 1:
-            return self.X.cpu().numpy()
-        counts = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
+            return X.cpu().numpy()
+        counts = torch.tensor([len(X)], dtype=torch.int64, device=self.device)
         every = torch.empty(self.world, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(every, counts, group=self.group)
         every = every.tolist()
         pad = max(every)
         mine = torch.zeros((pad, self.lanes), dtype=torch.float32, device=self.device)
-        mine[:self.n_owned] = self.X
+        mine[:len(X)] = X
         parts = torch.empty((self.world * pad, self.lanes), dtype=torch.float32,
                             device=self.device)
         dist.all_gather_into_tensor(parts, mine, group=self.group)
