@@ -50,8 +50,19 @@
 namespace yb {
 
 constexpr int SWEEP_THREADS = 128;
-constexpr int SWEEP_STAGE_CAP = 1536;  // staged pos4 records per round (<= 4095)
-constexpr int SWEEP_LIST_CAP = 32;     // neighbour-list entries per batch
+// Sizes of the staging window and of the per-thread list. Measured on B200 at
+// 1 M cells (profiles/r01_sweep_tuning.md): 1280 / 24 leaves ~60 KB of the SM's
+// 256 KB as L1 next to six resident CTAs, which the gathers of the accepted
+// pairs and of the user functor need more than a deeper window (1536 / 32:
+// growth step 2.25 ms -> 1.82 ms, others within 2 %).
+#ifndef YB_SWEEP_STAGE_CAP
+#define YB_SWEEP_STAGE_CAP 1280
+#endif
+#ifndef YB_SWEEP_LIST_CAP
+#define YB_SWEEP_LIST_CAP 24
+#endif
+constexpr int SWEEP_STAGE_CAP = YB_SWEEP_STAGE_CAP;  // staged pos4 records per round (<= 4095)
+constexpr int SWEEP_LIST_CAP = YB_SWEEP_LIST_CAP;    // neighbour-list entries per batch
 constexpr int SWEEP_ROWS = 9;
 constexpr size_t SWEEP_SMEM =
     size_t(SWEEP_STAGE_CAP) * sizeof(float4) +

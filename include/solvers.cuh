@@ -317,9 +317,19 @@ public:
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
     void dd_forces(int stage)
     {
+        cudaEvent_t sweep_start = nullptr, sweep_stop = nullptr;
+        if (profiling) {
+            YB_CUDA(cudaEventCreate(&sweep_start));
+            YB_CUDA(cudaEventCreate(&sweep_stop));
+        }
         Computer<Pt>::template pwints<pw_int, pw_friction, false>(stream, d_n,
             stage == 0 ? d_X : d_X1, d_old_v, stage == 0 ? d_dX : d_dX1,
-            d_partials, max_sweep_ctas, stage, yb::DRIFT_MEAN, 0, d_ctl, false);
+            d_partials, max_sweep_ctas, stage, yb::DRIFT_MEAN, 0, d_ctl, false,
+            sweep_start);
+        if (profiling) {
+            YB_CUDA(cudaEventRecord(sweep_stop, stream));
+            sweep_events.emplace_back(sweep_start, sweep_stop);
+        }
         YB_CUDA(cudaGetLastError());
     }
     // Predictor (stage 0) or corrector (stage 1) with the global drift d_mean
@@ -815,13 +825,30 @@ protected:
     template<typename Kernel>
     static int resident_ctas(Kernel kernel, int threads, size_t smem)
     {
+        // Tuning knobs (environment): YALLA_B200_SWEEP_CTAS caps the CTAs per SM
+        // the persistent grid is sized for; YALLA_B200_SWEEP_CARVEOUT sets the
+        // shared-memory share of the L1 in percent (what is left caches the
+        // gathers of the functor and of the accepted pairs).
         YB_CUDA(cudaFuncSetAttribute(kernel,
             cudaFuncAttributePreferredSharedMemoryCarveout,
             cudaSharedmemCarveoutMaxShared));
         int resident = 0;
         YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &resident, kernel, threads, smem));
-        return resident > 0 ? resident : 1;
+        const char* cap_env = getenv("YALLA_B200_SWEEP_CTAS");
+        if (cap_env && cap_env[0] && atoi(cap_env) > 0 && atoi(cap_env) < resident)
+            resident = atoi(cap_env);
+        if (resident < 1) resident = 1;
+        // Ask for no more shared memory than the resident CTAs need (+1 KB each
+        // that the driver reserves): the rest of the 256 KB stays L1.
+        const char* carveout_env = getenv("YALLA_B200_SWEEP_CARVEOUT");
+        int carveout = static_cast<int>(
+            (resident * (smem + 1024 + 512) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (carveout > 100) carveout = 100;
+        if (carveout_env && carveout_env[0]) carveout = atoi(carveout_env);
+        YB_CUDA(cudaFuncSetAttribute(kernel,
+            cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        return resident;
     }
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,

@@ -13,8 +13,10 @@ lib = yb.product() if impl == "product" else yb.reference()
 spec = bench.WORKLOADS[workload]
 X, types, gs = bench.make_state(spec, seed=1000)
 with bench.new_sim(lib, spec, X, types, gs) as sim:
-    sim.step(spec["dt"], 2)
+    sim.step(spec["dt"], 3)
     sim.sync()
-    ms, updates = sim.step_timed(spec["dt"], steps)
-    print(f"{workload} gs={gs} {impl}: {ms / steps:.3f} ms/step, "
-          f"{updates / ms / 1e6:.3f} G cell-updates/s")
+    repeats = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    for _ in range(repeats):
+        ms, updates = sim.step_timed(spec["dt"], steps)
+        print(f"{workload} gs={gs} {impl}: {ms / steps:.3f} ms/step, "
+              f"{updates / ms / 1e6:.3f} G cell-updates/s", flush=True)

@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(_ROOT, "yalla_b200", "_lib", "libyalla_b200.so")
+PRODUCT_LIB = os.environ.get("YALLA_B200_LIB") or os.path.join(
+    _ROOT, "yalla_b200", "_lib", "libyalla_b200.so")
 REFERENCE_LIB = os.path.join(_ROOT, "oracle", "_ref", "libyalla_ref.so")
 
 YB_OK, YB_EINVAL, YB_ECUDA, YB_ENOSYS = 0, -1, -2, -3
