@@ -476,7 +476,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
 // Tiles of the cube-order-free AoS state are staged to shared memory by the
 // whole CTA (plain loads: n is small wherever the Tile solver is used, and Pt
 // records are only 4-byte aligned, which rules out bulk copies).
-constexpr int TILE_THREADS = 64;
+#ifndef YB_TILE_THREADS
+#define YB_TILE_THREADS 128
+#endif
+#ifndef YB_TILE_UNROLL
+#define YB_TILE_UNROLL 4
+#endif
+constexpr int TILE_THREADS = YB_TILE_THREADS;
+constexpr int TILE_UNROLL = YB_TILE_UNROLL;
 
 template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
     float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
@@ -518,6 +525,7 @@ __global__ void __launch_bounds__(TILE_THREADS) sweep_tiles(
             __syncthreads();
 
             if (live) {
+#pragma unroll TILE_UNROLL
                 for (int q = 0; q < in_tile; q++) {
                     Pt Xj;
 #pragma unroll
