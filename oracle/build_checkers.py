@@ -22,7 +22,7 @@ from yalla_b200.build import NVCC_FLAGS, _newer, _run  # noqa: E402
 
 REFERENCE = os.environ.get("YALLA_REFERENCE", "/root/reference")
 UPSTREAM_TESTS = ["test_dtypes", "test_solvers", "test_links", "test_polarity",
-                  "test_inits", "test_vtk"]
+                  "test_inits", "test_vtk", "test_mesh"]
 
 
 def build_oracle():

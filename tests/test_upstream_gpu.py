@@ -6,6 +6,7 @@ do compile here, because Generic_forces also accepts the two-argument form and
 the polarity functions accept points.
 """
 import os
+import shutil
 import subprocess
 
 import pytest
@@ -16,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 BIN = os.path.join(ROOT, "tests", "_bin")
 TESTS = ["test_dtypes", "test_solvers", "test_links", "test_polarity",
-         "test_inits", "test_vtk"]
+         "test_inits", "test_vtk", "test_mesh"]
 
 
 @pytest.mark.parametrize("name", TESTS)
@@ -25,6 +26,12 @@ def test_upstream_suite(name, tmp_path):
     if not os.path.exists(binary):
         pytest.skip(f"{binary} was not built (needs /root/reference at build time)")
     env = dict(os.environ, YALLA_B200_SEED="7")
+    # test_mesh reads "tests/torus.vtk" relative to the working directory; the
+    # reference's fixture is not in this repository, scripts/make_torus.py
+    # generates an equivalent torus (R = 1, r = 0.5)
+    os.makedirs(tmp_path / "tests", exist_ok=True)
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "torus.vtk"),
+                tmp_path / "tests" / "torus.vtk")
     result = subprocess.run([binary], cwd=tmp_path, capture_output=True, text=True,
                             timeout=600, env=env)
     assert "ALL TESTS PASSED" in result.stdout, result.stdout[-2000:] + result.stderr[-2000:]
