@@ -193,6 +193,29 @@ public:
     }
     int get_d_n() { return Solver<Pt>::get_d_n(); }
 
+    // Extension: move only the n live cells, straight between the caller's
+    // buffer and the device, on the solver's stream (full PCIe rate if the
+    // buffer is pinned). upload() also sets the cell count; download() waits.
+    void upload(const Pt* h_src, int n)
+    {
+        assert(n <= n_max);
+        *h_n = n;
+        YB_CUDA(cudaMemcpyAsync(d_X, h_src, static_cast<size_t>(n) * sizeof(Pt),
+            cudaMemcpyHostToDevice, Solver<Pt>::stream));
+        YB_CUDA(cudaMemcpyAsync(
+            d_n, h_n, sizeof(int), cudaMemcpyHostToDevice, Solver<Pt>::stream));
+    }
+    int download(Pt* h_dst, int capacity)
+    {
+        const int n = get_d_n();
+        assert(n <= capacity);
+        YB_CUDA(cudaMemcpyAsync(h_dst, d_X, static_cast<size_t>(n) * sizeof(Pt),
+            cudaMemcpyDeviceToHost, Solver<Pt>::stream));
+        YB_CUDA(cudaStreamSynchronize(Solver<Pt>::stream));
+        *h_n = n;
+        return n;
+    }
+
     template<Pairwise_interaction<Pt> pw_int>
     void take_step(float dt, Generic_forces<Pt> gen_forces = no_gen_forces<Pt>)
     {

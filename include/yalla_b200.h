@@ -108,6 +108,16 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
 int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     int n_steps, float* h_out, int capacity, int* n_out);
 
+/* Extensions for pipelining independent batches (product library only): give
+ * a model its own CUDA stream (a cudaStream_t; default: the legacy default
+ * stream like every ya||a launch), and a host-buffer step that only ENQUEUES
+ * the upload of n cells, n_steps steps and the download of out_cells cells to
+ * h_out plus the final cell count to *h_n_out (both pinned). The caller waits
+ * on the stream before reading them. */
+int yb_sim_set_stream(yb_sim* sim, void* stream);
+int yb_sim_step_host_async(yb_sim* sim, const float* h_in, int n, float dt,
+    int n_steps, float* h_out, int out_cells, int* h_n_out);
+
 /* Time the dominant kernel (the pairwise sweep) with CUDA events on the
  * launching stream: enable, run steps, then read the accumulated milliseconds
  * and the number of sweep launches since the last read. Product library only

@@ -1015,6 +1015,15 @@ int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems)
 {
     return sim->slab_counts(n_owned, n_total, problems);
 }
+int yb_sim_set_stream(yb_sim*, void*)
+{
+    return fail(YB_ENOSYS, "streams need the product library");
+}
+int yb_sim_step_host_async(
+    yb_sim*, const float*, int, float, int, float*, int, int*)
+{
+    return fail(YB_ENOSYS, "asynchronous steps need the product library");
+}
 int yb_sim_profile_sweeps(yb_sim*, int)
 {
     return fail(YB_ENOSYS, "sweep profiling needs the product library");

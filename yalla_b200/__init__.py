@@ -83,6 +83,11 @@ SIGNATURES = {
                                       ctypes.c_float, ctypes.c_void_p]),
     "yb_slab_counts": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_int_p,
                                       _c_int_p]),
+    "yb_sim_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_sim_step_host_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_float,
+                                              ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_void_p]),
     "yb_sim_profile_sweeps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_sim_read_sweep_profile": (ctypes.c_int, [ctypes.c_void_p, _c_float_p,
                                                  _c_int_p]),
@@ -337,6 +342,18 @@ class Sim:
             self.handle, ctypes.byref(ms), ctypes.byref(launches)),
             "read_sweep_profile")
         return ms.value, launches.value
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: a cudaStream_t as int (e.g. torch.cuda.Stream().cuda_stream)"""
+        self.lib.check(self.lib.cdll.yb_sim_set_stream(self.handle, cuda_stream),
+                       "set_stream")
+
+    def step_host_async(self, X_in, dt, n_steps, X_out, out_cells, n_out_ptr):
+        """Enqueue upload, steps and download on the model's stream; X_in, X_out
+        and the int at n_out_ptr must be pinned host memory."""
+        self.lib.check(self.lib.cdll.yb_sim_step_host_async(
+            self.handle, X_in.ctypes.data, len(X_in), dt, n_steps,
+            X_out.ctypes.data, out_cells, n_out_ptr), "step_host_async")
 
     def n(self):
         n = ctypes.c_int()

@@ -62,6 +62,25 @@ struct yb_sim {
     }
     // One model step (asynchronous).
     virtual int step(float dt) = 0;
+    // Host buffers in, n_steps steps, host buffers out; waits.
+    virtual int step_host(const float* h_in, int n, float dt, int n_steps,
+        float* h_out, int capacity, int* n_out)
+    {
+        int status = set_state(h_in, n, 0);
+        if (status != YB_OK) return status;
+        for (int k = 0; k < n_steps; k++) step(dt);
+        return get_state(h_out, capacity, n_out);
+    }
+    // Extensions of the product library: a private stream per model, and a
+    // host-buffer step that only enqueues (for pipelining independent batches).
+    virtual int set_stream(void*)
+    {
+        return fail(YB_ENOSYS, "streams need the product library");
+    }
+    virtual int step_host_async(const float*, int, float, int, float*, int, int*)
+    {
+        return fail(YB_ENOSYS, "asynchronous steps need the product library");
+    }
     // Device address of the current cell count (for asynchronous snapshots).
     virtual const int* count_on_device() = 0;
     virtual int current_n() = 0;
@@ -166,7 +185,50 @@ struct Sim_base : yb_sim {
     }
     int current_n() override { return n_host = cells.get_d_n(); }
     const int* count_on_device() override { return cells.d_n; }
+    // stream the model's own kernels are launched on (the solver's stream)
+    cudaStream_t model_stream() const
+    {
 #ifdef YALLA_B200
+        return cells.stream;
+#else
+        return 0;
+#endif
+    }
+#ifdef YALLA_B200
+    int set_stream(void* stream) override
+    {
+        cells.stream = static_cast<cudaStream_t>(stream);
+        return YB_OK;
+    }
+    // Enqueue upload, steps and the download of `out_cells` cells plus the
+    // count (into pinned *h_n_out); the caller waits on the stream.
+    int step_host_async(const float* h_in, int n, float dt, int n_steps,
+        float* h_out, int out_cells, int* h_n_out) override
+    {
+        if (n < 0 || n > cells.n_max || out_cells > cells.n_max)
+            return fail(YB_EINVAL, "n > n_max");
+        cells.upload(reinterpret_cast<const Pt*>(h_in), n);
+        for (int k = 0; k < n_steps; k++) this->step(dt);
+        cudaMemcpyAsync(h_out, cells.d_X, sizeof(Pt) * size_t(out_cells),
+            cudaMemcpyDeviceToHost, cells.stream);
+        cudaMemcpyAsync(h_n_out, cells.d_n, sizeof(int), cudaMemcpyDeviceToHost,
+            cells.stream);
+        return check_cuda("yb_sim_step_host_async");
+    }
+    // n live cells straight between the caller's buffers and the device
+    // (Solution::copy_to_device/host move n_max cells through h_X)
+    int step_host(const float* h_in, int n, float dt, int n_steps, float* h_out,
+        int capacity, int* n_out) override
+    {
+        if (n < 0 || n > cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        cells.upload(reinterpret_cast<const Pt*>(h_in), n);
+        for (int k = 0; k < n_steps; k++) this->step(dt);
+        const int n_now = cells.get_d_n();
+        if (n_now > capacity) return fail(YB_EINVAL, "capacity < n");
+        n_host = cells.download(reinterpret_cast<Pt*>(h_out), capacity);
+        if (n_out) *n_out = n_host;
+        return check_cuda("yb_sim_step_host");
+    }
     int profile_sweeps(int enable) override
     {
         cells.profile_sweeps(enable != 0);
@@ -461,8 +523,10 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
     // n handed to the callback instead of reading d_n back.
     void reset_counters(int n)
     {
-        cudaMemsetAsync(n_mes_nbs.d_prop, 0, sizeof(int) * size_t(n));
-        cudaMemsetAsync(n_epi_nbs.d_prop, 0, sizeof(int) * size_t(n));
+        cudaMemsetAsync(
+            n_mes_nbs.d_prop, 0, sizeof(int) * size_t(n), this->model_stream());
+        cudaMemsetAsync(
+            n_epi_nbs.d_prop, 0, sizeof(int) * size_t(n), this->model_stream());
     }
 };
 
@@ -504,7 +568,7 @@ struct Growth_sim : Typed_sim<Po_cell> {
     {
         const int n_max = cells.n_max;
         if (!seeded) {
-            setup_rand_states<<<(n_max + 128 - 1) / 128, 128>>>(
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, model_stream()>>>(
                 n_max, seed, d_state);
             seeded = true;
         }
@@ -514,8 +578,10 @@ struct Growth_sim : Typed_sim<Po_cell> {
         cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
         if (prolif_rate > 0) {
             // sized for the capacity; the kernel reads the live count itself
-            models::snapshot_count<<<1, 1>>>(cells.d_n, d_n_at_launch);
-            models::proliferate<<<(n_max + 128 - 1) / 128, 128>>>(prolif_rate,
+            models::snapshot_count<<<1, 1, 0, model_stream()>>>(
+                cells.d_n, d_n_at_launch);
+            models::proliferate<<<(n_max + 128 - 1) / 128, 128, 0,
+                model_stream()>>>(prolif_rate,
                 mean_dist, n_max, d_state, cells.d_X, cells.d_old_v, cells.d_n,
                 d_n_at_launch);
         }
@@ -770,10 +836,18 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
 int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     int n_steps, float* h_out, int capacity, int* n_out)
 {
-    int status = sim->set_state(h_in, n, 0);
-    if (status != YB_OK) return status;
-    for (int k = 0; k < n_steps; k++) sim->step(dt);
-    return sim->get_state(h_out, capacity, n_out);
+    return sim->step_host(h_in, n, dt, n_steps, h_out, capacity, n_out);
+}
+
+int yb_sim_set_stream(yb_sim* sim, void* stream)
+{
+    return sim->set_stream(stream);
+}
+
+int yb_sim_step_host_async(yb_sim* sim, const float* h_in, int n, float dt,
+    int n_steps, float* h_out, int out_cells, int* h_n_out)
+{
+    return sim->step_host_async(h_in, n, dt, n_steps, h_out, out_cells, h_n_out);
 }
 
 int yb_dd_load(yb_sim* sim, int stage, const float* X_owned,
