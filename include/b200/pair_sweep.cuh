@@ -49,25 +49,28 @@
 
 namespace yb {
 
+// Sizes of the staging window, of the per-thread list, and the CTAs per SM the
+// register budget is set for -- chosen per point type (measured on B200 at 1 M
+// cells, profiles/r01_sweep_tuning.md):
+//  * plain positions (float3/float4, cheap functors): 1024 / 24 and 8 resident
+//    CTAs -- the sweep is issue bound and more warps help (step 0.538 -> 0.503);
+//  * points with extra lanes (polarities, concentrations: heavy functors that
+//    gather their own per-cell arrays): 1280 / 24 and 6 CTAs, which leaves
+//    ~60 KB of the SM's 256 KB as L1 for those gathers (growth step 2.25 ms
+//    with 1536 / 32 -> 1.82 ms; 8 CTAs: 2.21 ms).
 constexpr int SWEEP_THREADS = 128;
-// Sizes of the staging window and of the per-thread list. Measured on B200 at
-// 1 M cells (profiles/r01_sweep_tuning.md): 1280 / 24 leaves ~60 KB of the SM's
-// 256 KB as L1 next to six resident CTAs, which the gathers of the accepted
-// pairs and of the user functor need more than a deeper window (1536 / 32:
-// growth step 2.25 ms -> 1.82 ms, others within 2 %).
-#ifndef YB_SWEEP_STAGE_CAP
-#define YB_SWEEP_STAGE_CAP 1280
-#endif
-#ifndef YB_SWEEP_LIST_CAP
-#define YB_SWEEP_LIST_CAP 24
-#endif
-constexpr int SWEEP_STAGE_CAP = YB_SWEEP_STAGE_CAP;  // staged pos4 records per round (<= 4095)
-constexpr int SWEEP_LIST_CAP = YB_SWEEP_LIST_CAP;    // neighbour-list entries per batch
 constexpr int SWEEP_ROWS = 9;
-constexpr size_t SWEEP_SMEM =
-    size_t(SWEEP_STAGE_CAP) * sizeof(float4) +
-    size_t(SWEEP_ROWS) * SWEEP_THREADS * sizeof(uint32_t) +
-    size_t(SWEEP_LIST_CAP) * SWEEP_THREADS * sizeof(uint16_t);
+
+template<int LANES>
+struct Sweep_config {
+    static constexpr int stage_cap = LANES <= 4 ? 1024 : 1280;  // <= 4095
+    static constexpr int list_cap = 24;
+    static constexpr int min_ctas = LANES <= 4 ? 8 : 6;
+    static constexpr size_t smem =
+        size_t(stage_cap) * sizeof(float4) +
+        size_t(SWEEP_ROWS) * SWEEP_THREADS * sizeof(uint32_t) +
+        size_t(list_cap) * SWEEP_THREADS * sizeof(uint16_t);
+};
 // Squared-distance pre-filter: keep everything the exact test could accept.
 // The rounding error of dx*dx+dy*dy+dz*dz is a few 1e-7 relative; 1e-5 is
 // generous and costs practically no extra list entries.
@@ -282,7 +285,8 @@ __device__ __forceinline__ void finish_drift(float3 my_partial,
 // otherwise d_dX is write-only (no zero fill anywhere).
 template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
     float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
-__global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
+__global__ void __launch_bounds__(
+    SWEEP_THREADS, Sweep_config<Layout<Pt>::lanes>::min_ctas) sweep_cubes(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
     const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
@@ -290,6 +294,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 6) sweep_cubes(
     int fix_point, Step_ctl* ctl)
 {
     using L = Layout<Pt>;
+    constexpr int SWEEP_STAGE_CAP = Sweep_config<L::lanes>::stage_cap;
+    constexpr int SWEEP_LIST_CAP = Sweep_config<L::lanes>::list_cap;
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     float4* s_pos = reinterpret_cast<float4*>(sweep_smem);
     uint32_t* s_range = reinterpret_cast<uint32_t*>(s_pos + SWEEP_STAGE_CAP);

@@ -880,7 +880,7 @@ protected:
     {
         static const int ctas_per_sm =
             resident_ctas(yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>,
-                yb::SWEEP_THREADS, yb::SWEEP_SMEM);
+                yb::SWEEP_THREADS, yb::Sweep_config<yb::Layout<Pt>::lanes>::smem);
         return ctas_per_sm;
     }
 
@@ -923,7 +923,8 @@ protected:
             prepare<pw_int, pw_friction, SEEDED>(), yb::SWEEP_THREADS, max_ctas);
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
-            <<<ctas, yb::SWEEP_THREADS, yb::SWEEP_SMEM, s>>>(d_n, n_max, pos4,
+            <<<ctas, yb::SWEEP_THREADS,
+                yb::Sweep_config<yb::Layout<Pt>::lanes>::smem, s>>>(d_n, n_max, pos4,
                 aux, cube_sorted, sort.offset, cube_size, grid_size, active_cubes,
                 d_dX, d_partials, stage, drift_mode, fix_point, d_ctl);
     }
