@@ -56,6 +56,14 @@ WORKLOADS = {
                     dt=0.1, params={}, typed=False),
     "relu_10M": dict(model="relu_grid", n=10_000_000, n_max=10_000_000, d=0.8,
                      dt=0.1, params={}, typed=False),
+    # configs[3]'s ingredients at 1 M cells: 7-float branching cell (Turing
+    # reaction-diffusion + bending + atomic neighbour counters), and protrusion
+    # links as generic force (one link per cell)
+    "branching_1M": dict(model="branching", n=1_000_000, n_max=1_000_000, d=0.75,
+                         dt=0.2, params={}, typed=True),
+    "protrusions_1M": dict(model="protrusions", n=1_000_000, n_max=1_000_000,
+                           d=0.8, dt=0.1, params={"link_strength": 0.2},
+                           typed=False, links_per_cell=1),
     "growth_100k": dict(model="growth", n=100_000, n_max=262_144, d=0.75,
                         dt=0.2, params={"prolif_rate": 0.006, "mean_dist": 0.75,
                                         "seed": 2}, typed=True),
@@ -75,8 +83,11 @@ def make_state(spec, seed):
     if lanes == 3:
         X = workloads.lattice_ball(spec["n"], spec["d"], rng)
     else:
-        X = workloads.polarized_ball(spec["n"], spec["d"], rng, lattice=True,
-                                     noise=0.0 if spec["typed"] else 0.5)
+        X = np.zeros((spec["n"], lanes), dtype=np.float32)
+        X[:, :5] = workloads.polarized_ball(spec["n"], spec["d"], rng, lattice=True,
+                                            noise=0.0 if spec["typed"] else 0.5)
+        if lanes > 5:  # morphogen concentrations u, v
+            X[:, 5:] = rng.random((spec["n"], lanes - 5)).astype(np.float32) * 0.2
     types = None
     if spec["typed"]:
         types = workloads.shell_types(X)
@@ -92,6 +103,9 @@ def new_sim(lib, spec, X, types, gs):
         sim.set_param(key, value)
     if types is not None:
         sim.set_ints("type", types)
+    if spec.get("links_per_cell"):
+        sim.set_links(workloads.random_links(
+            X, spec["links_per_cell"] * len(X), 2.0, np.random.default_rng(77)))
     sim.set_state(X)
     return sim
 

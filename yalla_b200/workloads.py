@@ -82,15 +82,20 @@ def shell_types(X, thickness=1.0):
     return (r > r.max() - thickness).astype(np.int32)
 
 
-def random_links(X, n_links, max_dist, rng):
+def random_links(X, n_links, max_dist, rng, k=12):
     """n_links pairs (a, b), a != b, of cells closer than max_dist -- what a
-    protrusion-update kernel produces (examples/sorting_prot.cu:33-74)."""
+    protrusion-update kernel produces (examples/sorting_prot.cu:33-74). Each
+    link joins a random cell with a random one of its k nearest neighbours
+    inside max_dist; links that find none stay inactive (a == b == 0)."""
     from scipy.spatial import cKDTree
     tree = cKDTree(X[:, :3])
-    links = np.zeros((n_links, 2), dtype=np.int32)
     a = rng.integers(0, len(X), size=n_links)
-    for k, cell in enumerate(a):
-        near = [j for j in tree.query_ball_point(X[cell, :3], max_dist) if j != cell]
-        if near:
-            links[k] = (cell, near[rng.integers(0, len(near))])
+    distance, index = tree.query(X[a, :3], k=k + 1, distance_upper_bound=max_dist,
+                                 workers=-1)
+    pick = rng.integers(1, k + 1, size=n_links)  # column 0 is the cell itself
+    b = index[np.arange(n_links), pick]
+    found = np.isfinite(distance[np.arange(n_links), pick]) & (b < len(X)) & (b != a)
+    links = np.zeros((n_links, 2), dtype=np.int32)
+    links[found, 0] = a[found]
+    links[found, 1] = b[found]
     return links
