@@ -575,4 +575,108 @@ __global__ void __launch_bounds__(TILE_THREADS) sweep_tiles(
         fix_point, d_dX, ctl, s_red);
 }
 
+
+// ---- Tile solver sweep, pairs split across lanes (opt-in) ----------------------
+// With a few hundred cells, one thread per cell leaves the machine idle and
+// every thread with a chain of n dependent pair evaluations. Here a group of G
+// lanes shares one cell i: lane g takes the partners j = g, g + G, ... and the
+// partial sums are combined by a fixed shuffle tree (deterministic, but a
+// different summation order than the reference). The functor runs in G
+// threads per cell, so this is only valid for functors WITHOUT per-cell side
+// effects; it is enabled per solver with `cells.split_pairs = true`.
+template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
+    float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED, int G>
+__global__ void __launch_bounds__(TILE_THREADS) sweep_tiles_split(
+    const int* __restrict__ d_n, int n_max, const Pt* __restrict__ d_X,
+    const float3* __restrict__ d_old_v, Pt* d_dX, float* __restrict__ partials,
+    int stage, int drift_mode, int fix_point, Step_ctl* ctl)
+{
+    using L = Layout<Pt>;
+    constexpr int CELLS = TILE_THREADS / G;  // cells per CTA and chunk
+    __shared__ float s_X[TILE_THREADS * L::lanes];
+    __shared__ float s_v[TILE_THREADS * 3];
+    __shared__ float s_red[3][TILE_THREADS / 32];
+
+    const int t = threadIdx.x, g = t % G;
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, CELLS);
+    float3 cta_sum{0.f, 0.f, 0.f};
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int i = chunk * CELLS + t / G;
+        const bool live = i < n;
+        Pt Xi{0};
+        if (live) Xi = load_pt(d_X, i);
+        Pt F{0};
+        float3 sum_v{0.f, 0.f, 0.f};
+        float sum_friction = 0.f;
+
+        for (int tile_start = 0; tile_start < n; tile_start += TILE_THREADS) {
+            const int in_tile = min(TILE_THREADS, n - tile_start);
+            __syncthreads();
+            const float* src_X = reinterpret_cast<const float*>(d_X + tile_start);
+            for (int q = t; q < in_tile * L::lanes; q += TILE_THREADS)
+                s_X[q] = __ldg(src_X + q);
+            const float* src_v =
+                reinterpret_cast<const float*>(d_old_v + tile_start);
+            for (int q = t; q < in_tile * 3; q += TILE_THREADS)
+                s_v[q] = __ldg(src_v + q);
+            __syncthreads();
+
+            if (live) {
+                for (int q = g; q < in_tile; q += G) {
+                    Pt Xj;
+#pragma unroll
+                    for (int l = 0; l < L::lanes; l++)
+                        lane(Xj, l) = s_X[q * L::lanes + l];
+                    const int j = tile_start + q;
+                    const Pt rij = Xi - Xj;
+                    const float dist = norm3df(rij.x, rij.y, rij.z);
+                    F += pw_int(Xi, rij, dist, i, j);
+                    const float friction = pw_friction(Xi, rij, dist, i, j);
+                    sum_friction += friction;
+                    if (friction != 0.f)
+                        sum_v += friction *
+                                 float3{s_v[3 * q], s_v[3 * q + 1], s_v[3 * q + 2]};
+                }
+            }
+        }
+
+        // combine the G partial sums of every cell (all lanes take part)
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) {
+#pragma unroll
+            for (int l = 0; l < L::lanes; l++)
+                lane(F, l) += __shfl_xor_sync(0xffffffffu, lane(F, l), d);
+            sum_v.x += __shfl_xor_sync(0xffffffffu, sum_v.x, d);
+            sum_v.y += __shfl_xor_sync(0xffffffffu, sum_v.y, d);
+            sum_v.z += __shfl_xor_sync(0xffffffffu, sum_v.z, d);
+            sum_friction += __shfl_xor_sync(0xffffffffu, sum_friction, d);
+        }
+
+        float3 mine{0.f, 0.f, 0.f};
+        if (live && g == 0) {
+            Pt dX = F;
+            if (SEEDED) {
+                dX = load_pt_rw(d_dX, i);
+                dX += F;
+            }
+            if (sum_friction > 0) {
+                dX.x += sum_v.x / sum_friction;
+                dX.y += sum_v.y / sum_friction;
+                dX.z += sum_v.z / sum_friction;
+            }
+            store_pt(d_dX, i, dX);
+            mine = float3{dX.x, dX.y, dX.z};
+        }
+        __syncthreads();
+        const float3 chunk_sum =
+            block_sum3<TILE_THREADS>(mine.x, mine.y, mine.z, s_red);
+        cta_sum.x += chunk_sum.x, cta_sum.y += chunk_sum.y, cta_sum.z += chunk_sum.z;
+    }
+
+    finish_drift<TILE_THREADS>(cta_sum, partials, n, stage, drift_mode,
+        fix_point, d_dX, ctl, s_red);
+}
+
 }  // namespace yb

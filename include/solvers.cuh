@@ -631,8 +631,15 @@ class Tile_computer {
 public:
     Tile_computer(int n_max) : n_max{n_max} {}
 
+    // Extension: split the partners of every cell across 8 or 32 lanes
+    // (b200/pair_sweep.cuh, sweep_tiles_split). Much faster for the few hundred
+    // to few thousand cells the Tile solver is used with, but the pairwise
+    // functor then runs in several threads per cell: only for functors without
+    // per-cell side effects. Off by default.
+    bool split_pairs = false;
+
 protected:
-    float graph_key() const { return 0.f; }
+    float graph_key() const { return split_pairs ? 1.f : 0.f; }
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
         bool SEEDED>
@@ -646,10 +653,34 @@ protected:
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
         bool /*binned_by_predictor*/, cudaEvent_t before_sweep = nullptr)
     {
-        int blocks = yb::ceil_div(n_max > 0 ? n_max : 1, yb::TILE_THREADS);
-        if (blocks > max_ctas) blocks = max_ctas;
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
-        yb::sweep_tiles<Pt, pw_int, pw_friction, SEEDED>
+        const int cells = n_max > 0 ? n_max : 1;
+        if (split_pairs && cells <= 2048) {
+            launch_split<pw_int, pw_friction, SEEDED, 32>(s, cells, max_ctas, d_n,
+                d_X, d_old_v, d_dX, d_partials, stage, drift_mode, fix_point,
+                d_ctl);
+        } else if (split_pairs && cells <= 16384) {
+            launch_split<pw_int, pw_friction, SEEDED, 8>(s, cells, max_ctas, d_n,
+                d_X, d_old_v, d_dX, d_partials, stage, drift_mode, fix_point,
+                d_ctl);
+        } else {
+            int blocks = yb::ceil_div(cells, yb::TILE_THREADS);
+            if (blocks > max_ctas) blocks = max_ctas;
+            yb::sweep_tiles<Pt, pw_int, pw_friction, SEEDED>
+                <<<blocks, yb::TILE_THREADS, 0, s>>>(d_n, n_max, d_X, d_old_v,
+                    d_dX, d_partials, stage, drift_mode, fix_point, d_ctl);
+        }
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED, int G>
+    void launch_split(cudaStream_t s, int cells, int max_ctas, const int* d_n,
+        const Pt* d_X, const float3* d_old_v, Pt* d_dX, float* d_partials,
+        int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl)
+    {
+        int blocks = yb::ceil_div(cells, yb::TILE_THREADS / G);
+        if (blocks > max_ctas) blocks = max_ctas;
+        yb::sweep_tiles_split<Pt, pw_int, pw_friction, SEEDED, G>
             <<<blocks, yb::TILE_THREADS, 0, s>>>(d_n, n_max, d_X, d_old_v, d_dX,
                 d_partials, stage, drift_mode, fix_point, d_ctl);
     }

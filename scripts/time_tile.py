@@ -6,7 +6,12 @@ from yalla_b200 import workloads
 rng = np.random.default_rng(1)
 lib = yb.product()
 for model, X, dt in (("springs", workloads.random_ball(800, 0.5, rng), 0.001), ("spring_tile", workloads.random_ball(5000, 0.8, rng), 0.05)):
-    with lib.sim(model, len(X), 50, 1.0) as sim:
-        sim.set_state(X); sim.step(dt, 20); sim.sync()
-        best = min(sim.step_timed(dt, 200)[0] / 200 for _ in range(3))
-        print(f"{model} n={len(X)}: {best*1e3:.1f} us/step", flush=True)
+    ends = {}
+    for split in (0, 1):
+        with lib.sim(model, len(X), 50, 1.0) as sim:
+            sim.set_param("split_pairs", split)
+            sim.set_state(X); sim.step(dt, 20); sim.sync()
+            best = min(sim.step_timed(dt, 200)[0] / 200 for _ in range(3))
+            ends[split] = sim.get_state()
+            print(f"{model} n={len(X)} split={split}: {best*1e3:.1f} us/step", flush=True)
+    print("  max |split - plain| after 620 steps:", np.abs(ends[1] - ends[0]).max())

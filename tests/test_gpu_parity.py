@@ -172,6 +172,30 @@ def test_tile_and_grid_agree(product):
     assert_states_close(out[1], out[0], 2, "grid vs tile")
 
 
+@pytest.mark.parametrize("model,n,dt", [
+    ("springs", 800, 0.001), ("springs", 3, 0.001), ("spring_tile", 33, 0.05),
+    ("relu_tile", 2048, 0.05), ("relu_tile", 2049, 0.05), ("spring_tile", 5000, 0.05)])
+def test_tile_split_pairs_matches_oracle(product, oracle, model, n, dt):
+    # Tile_computer::split_pairs (extension): several lanes share one cell and
+    # sum in a different, fixed order -- same tolerance as every other path,
+    # and the same bits from run to run.
+    X = workloads.random_ball(n, 0.8, np.random.default_rng(n))
+    with oracle.sim(model, n) as sim:
+        sim.set_state(X)
+        sim.step(dt, 5)
+        want = sim.get_state()
+    got = []
+    for split in (1, 1, 0):  # on by default for these models; 0 = one thread per cell
+        with product.sim(model, n) as sim:
+            sim.set_param("split_pairs", split)
+            sim.set_state(X)
+            sim.step(dt, 5)
+            got.append(sim.get_state())
+    assert_states_close(got[0], want, 5, f"split {model} n={n}", 4.0)
+    assert_states_close(got[2], want, 5, f"plain {model} n={n}", 4.0)
+    assert np.array_equal(got[0], got[1])
+
+
 def test_cube_size_limits_interactions(product, oracle):
     # tests/test_solvers.cu:318-336: cube_size 0.5 hides a neighbour at 0.75
     X = np.array([[0, 0, 0], [0.75, 0, 0]], dtype=np.float32)

@@ -375,10 +375,25 @@ struct Spring_sim : Sim_base<float3, Solver> {
     Spring_sim(int n_max, Args... args) : Base{n_max, args...}
     {
         set_spring_length(0.5);
+#ifdef YALLA_B200
+        // the functors of these models are pure, so the Tile solver may share
+        // one cell between several lanes (solvers.cuh, Tile_computer);
+        // set_param("split_pairs", 0) switches back to one thread per cell
+        if constexpr (std::is_same<Solver<float3>, Tile_solver<float3>>::value)
+            this->cells.split_pairs = true;
+#endif
     }
     int set_param(const std::string& name, double value) override
     {
         if (name == "spring_length") return set_spring_length(value);
+#ifdef YALLA_B200
+        if constexpr (std::is_same<Solver<float3>, Tile_solver<float3>>::value) {
+            if (name == "split_pairs") {
+                this->cells.split_pairs = value != 0;
+                return YB_OK;
+            }
+        }
+#endif
         const int fixed = Base::set_fix(name, value);
         return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
     }
