@@ -76,6 +76,12 @@ struct Sweep_config {
 // generous and costs practically no extra list entries.
 constexpr float SWEEP_PREFILTER_SLACK = 1.00001f;
 
+// Cube trimming (sweep_cubes): squared gaps are compared against this, in units
+// of cube_size^2; the gaps themselves are shortened by SWEEP_TRIM_MARGIN cube
+// sizes, far more than the rounding of x / cube_size at |x| <= 512 cubes.
+constexpr float SWEEP_TRIM_LIMIT = 1.0001f;
+constexpr float SWEEP_TRIM_MARGIN = 1e-3f;
+
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
@@ -142,6 +148,37 @@ __device__ __forceinline__ int row_shift(int r, int grid_size)
 __device__ __forceinline__ int clamp_cube(int c, int n_cubes)
 {
     return c < 0 ? 0 : (c > n_cubes ? n_cubes : c);
+}
+
+// Squared distance (in cube sizes) from a cell to the neighbouring cubes along
+// each axis, as lower bounds: [axis][0] = 0 (same layer), [1] towards -1, [2]
+// towards +1. The fractions come from the very quotients cube_of() floors, so
+// they are consistent with the binning. A cell whose cube id was clamped (out
+// of the grid) is not where its id says: no trimming for it.
+__device__ __forceinline__ void trim_gaps(const float4& me, float cube_size,
+    int grid_size, int z_half, int my_cube, float (*gap2)[3])
+{
+    const float q[3] = {me.x / cube_size, me.y / cube_size, me.z / cube_size};
+    float fl[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        fl[c] = floorf(q[c]);
+        const float f = q[c] - fl[c];
+        const float below = fmaxf(f - SWEEP_TRIM_MARGIN, 0.f);
+        const float above = fmaxf(1.f - f - SWEEP_TRIM_MARGIN, 0.f);
+        gap2[c][0] = 0.f;
+        gap2[c][1] = below * below;
+        gap2[c][2] = above * above;
+    }
+    const long long half = grid_size / 2;
+    const long long id = (static_cast<long long>(fl[0]) + half) +
+                         (static_cast<long long>(fl[1]) + half) * grid_size +
+                         (static_cast<long long>(fl[2]) + z_half) *
+                             grid_size * grid_size;
+    if (id != my_cube) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) gap2[c][1] = gap2[c][2] = 0.f;
+    }
 }
 
 template<typename Pt>
@@ -289,9 +326,9 @@ __global__ void __launch_bounds__(
     SWEEP_THREADS, Sweep_config<Layout<Pt>::lanes>::min_ctas) sweep_cubes(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
-    const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
-    Pt* d_dX, float* __restrict__ partials, int stage, int drift_mode,
-    int fix_point, Step_ctl* ctl)
+    const int* __restrict__ offset, float cube_size, int grid_size, int z_half,
+    int n_cubes, Pt* d_dX, float* __restrict__ partials, int stage,
+    int drift_mode, int fix_point, Step_ctl* ctl)
 {
     using L = Layout<Pt>;
     constexpr int SWEEP_STAGE_CAP = Sweep_config<L::lanes>::stage_cap;
@@ -340,12 +377,23 @@ __global__ void __launch_bounds__(
         }
         // This thread's candidate slots per row, as global slot numbers. The 18
         // loads are independent and fly while the spans are being staged.
+        // Cubes that lie entirely beyond the cut-off are trimmed: a cell sits at
+        // fraction f of its cube, so everything in the cube at offset -1 (+1)
+        // along an axis is at least f (1 - f) cube sizes away along that axis.
+        // That drops about a quarter of the candidates (corner cubes half of
+        // the time, edge cubes a fifth) and never a pair the exact test accepts.
+        float gap2[3][3];  // [axis][0: same, 1: -1, 2: +1], in cube_size^2
+        trim_gaps(me, cube_size, grid_size, z_half, my_cube, gap2);
         int my_lo[SWEEP_ROWS], my_hi[SWEEP_ROWS];
 #pragma unroll
         for (int r = 0; r < SWEEP_ROWS; r++) {
             const int c = my_cube + row_shift(r, grid_size);
-            my_lo[r] = live ? __ldg(offset + clamp_cube(c - 1, n_cubes)) : 0;
-            my_hi[r] = live ? __ldg(offset + clamp_cube(c + 2, n_cubes)) : 0;
+            const float row_gap2 = gap2[1][r % 3] + gap2[2][r / 3];
+            const bool row_out = !live || row_gap2 >= SWEEP_TRIM_LIMIT;
+            const int first = row_gap2 + gap2[0][1] >= SWEEP_TRIM_LIMIT ? c : c - 1;
+            const int last = row_gap2 + gap2[0][2] >= SWEEP_TRIM_LIMIT ? c + 1 : c + 2;
+            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, n_cubes));
+            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, n_cubes));
         }
         __syncthreads();
         if (t == 0) {
@@ -397,37 +445,43 @@ __global__ void __launch_bounds__(
             mbar_wait(&s_bar, parity);
             parity ^= 1u;
 
-            // -- phase 1 (scan) and phase 2 (interact). One pass unless a list
-            //    overflows; then the scan resumes where it stopped.
-            int r0 = 0, a0 = -1;
+            // -- phase 1 (scan) and phase 2 (interact). The scan is branch free:
+            //    a hit is stored if its number falls into [base, base + CAP) and
+            //    counted in any case. One pass unless a list overflows; then the
+            //    scan resumes at the row where it did, with the next base.
+            int r_start = 0, count_start = 0, base = 0;
             bool pending = owned;
             while (pending) {
-                int listed = 0;
+                int slot = count_start - base;  // number of the next hit - base
+                uint16_t* lp = s_list + (slot * SWEEP_THREADS + t);
                 pending = false;
-                for (int r = r0; r < SWEEP_ROWS; r++) {
+                for (int r = r_start; r < SWEEP_ROWS; r++) {
                     const uint32_t range = s_range[r * SWEEP_THREADS + t];
-                    int a = (r == r0 && a0 >= 0) ? a0 : int(range & 0xffffu);
-                    const int b = int(range >> 16);
-                    const uint16_t tag = uint16_t(r << 12);
-                    for (; a < b; a++) {
-                        const float4 p = s_pos[a];
+                    const uint32_t tag = uint32_t(r) << 12;
+                    // the list entry doubles as loop counter
+                    uint32_t entry = tag | (range & 0xffffu);
+                    const uint32_t entry_end = tag | (range >> 16);
+                    const float4* pp = s_pos + (range & 0xffffu);
+                    const int slot_at_row = slot;
+#pragma unroll 2
+                    for (; entry < entry_end; entry++, pp++) {
+                        const float4 p = *pp;
                         const float dx = me.x - p.x, dy = me.y - p.y,
                                     dz = me.z - p.z;
                         const float d2 = dx * dx + dy * dy + dz * dz;
-                        if (!(d2 > reach2)) {
-                            if (listed == SWEEP_LIST_CAP) {
-                                pending = true;
-                                break;
-                            }
-                            s_list[listed * SWEEP_THREADS + t] = tag | uint16_t(a);
-                            listed++;
-                        }
+                        const bool hit = !(d2 > reach2);
+                        if (hit && unsigned(slot) < unsigned(SWEEP_LIST_CAP))
+                            *lp = uint16_t(entry);
+                        if (hit) slot++, lp += SWEEP_THREADS;
                     }
-                    if (pending) {
-                        r0 = r, a0 = a;
+                    if (slot > SWEEP_LIST_CAP) {
+                        pending = true;
+                        r_start = r, count_start = base + slot_at_row;
                         break;
                     }
                 }
+                const int listed = min(max(slot, 0), SWEEP_LIST_CAP);
+                base += SWEEP_LIST_CAP;
 
                 for (int e = 0; e < listed; e++) {
                     const unsigned entry = s_list[e * SWEEP_THREADS + t];

@@ -956,8 +956,9 @@ protected:
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::SWEEP_THREADS,
                 yb::Sweep_config<yb::Layout<Pt>::lanes>::smem, s>>>(d_n, n_max, pos4,
-                aux, cube_sorted, sort.offset, cube_size, grid_size, active_cubes,
-                d_dX, d_partials, stage, drift_mode, fix_point, d_ctl);
+                aux, cube_sorted, sort.offset, cube_size, grid_size, z_half,
+                active_cubes, d_dX, d_partials, stage, drift_mode, fix_point,
+                d_ctl);
     }
 
     void predict(cudaStream_t s, int blocks, const int* d_n, float dt,
