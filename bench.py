@@ -64,6 +64,9 @@ WORKLOADS = {
     "protrusions_1M": dict(model="protrusions", n=1_000_000, n_max=1_000_000,
                            d=0.8, dt=0.1, params={"link_strength": 0.2},
                            typed=False, links_per_cell=1),
+    # configs[3] at its named size on one GPU (Cell = 28 B, n_max 12.5 M)
+    "branching_10M": dict(model="branching", n=10_000_000, n_max=10_000_000,
+                          d=0.75, dt=0.2, params={}, typed=True),
     "growth_100k": dict(model="growth", n=100_000, n_max=262_144, d=0.75,
                         dt=0.2, params={"prolif_rate": 0.006, "mean_dist": 0.75,
                                         "seed": 2}, typed=True),
@@ -176,6 +179,47 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
                 "sm_max_mhz": self.sm_max, "samples": len(self.sm),
                 "reasons": sorted(self.reasons)}
+
+
+# FP32 lane-instructions of the pairwise functors per accepted pair (SURVEY.md
+# 8(d): counted from the SASS of the reference build; bending-type functors
+# include their MUFU expansions). The growth functor bends only epithelium-
+# epithelium pairs, a thin shell of the tissue.
+FUNCTOR_LANE_INSTR = {"relu_grid": 12, "spring_grid": 8, "protrusions": 12,
+                      "growth": 20, "epithelium": 250, "branching": 270}
+
+
+def pair_statistics(X, cube_size=1.0, sample=200_000):
+    """Exact mean number of candidates (cells in the 27 surrounding cubes, self
+    included) and of accepted pairs (distance < cube_size, self included) per
+    cell -- the C and N of SURVEY.md 8(d). Candidates from the cube histogram
+    of the whole tissue, accepted pairs on a random sample of cells."""
+    from scipy.ndimage import uniform_filter
+    from scipy.spatial import cKDTree
+    pos = X[:, :3].astype(np.float64)
+    cube = np.floor(pos / cube_size).astype(np.int64)
+    cube -= cube.min(axis=0) - 1
+    shape = tuple(cube.max(axis=0) + 2)
+    counts = np.zeros(shape, dtype=np.float64)
+    np.add.at(counts, (cube[:, 0], cube[:, 1], cube[:, 2]), 1.0)
+    around = uniform_filter(counts, size=3, mode="constant") * 27.0
+    candidates = float(np.rint(around[cube[:, 0], cube[:, 1], cube[:, 2]]).mean())
+    tree = cKDTree(pos)
+    pick = np.random.default_rng(5).choice(len(pos), size=min(sample, len(pos)),
+                                           replace=False)
+    accepted = tree.query_ball_point(pos[pick], cube_size * (1 - 1e-7),
+                                     return_length=True, workers=-1)
+    return candidates, float(np.mean(accepted))
+
+
+def sweep_traffic(workload):
+    """DRAM bytes per sweep_cubes launch from the committed `ncu --set full`
+    capture of this workload (profiles/r01_sweep_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
+    if not os.path.exists(path):
+        return None
+    entry = json.load(open(path)).get(workload)
+    return None if entry is None else entry["dram_bytes_per_launch"]
 
 
 def cpu_baseline(spec, steps=2, sample_cells=200_000):
@@ -493,12 +537,30 @@ def main():
         roofline = {"bound": "hbm", "kernel": "sweep_cubes",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_kind": peak_kind,
-                    "traffic": None, "avg_launch_ms": avg_ms,
+                    "traffic": sweep_traffic(args.workload),
+                    "avg_launch_ms": avg_ms,
                     "share_of_step": 2 * avg_ms / (ms / steps),
                     "step_frac": value / world * (9 * LANES_BYTES[lanes] + 36)
                     / 1e9 / peak,
                     "note": "instruction-issue bound, not HBM bound; see "
-                            "DESIGN.md and profiles/"}
+                            "fp32_issue, DESIGN.md and profiles/"}
+        if rank == 0:
+            # the second ceiling of SURVEY.md 8(d): algorithmic FP32 lane-
+            # instructions per sweep and cell, I = C * 7 + N * (13 + f_pw),
+            # against the microbenchmarked FP32 issue rate of the chip
+            candidates, accepted = pair_statistics(X)
+            per_cell = candidates * 7 + accepted * (
+                13 + FUNCTOR_LANE_INSTR[spec["model"]])
+            fp32_peak = json.load(open(os.path.join(
+                ROOT, "profiles", "r01_microbench_peaks.json")))[
+                    "fp32_lane_instr_per_s_T"] * 1e12
+            fp32_achieved = per_cell * cells_per_launch / (avg_ms * 1e-3)
+            roofline["fp32_issue"] = {
+                "candidates_per_cell": candidates, "accepted_per_cell": accepted,
+                "lane_instr_per_cell_and_sweep": per_cell,
+                "achieved": fp32_achieved / 1e12, "peak": fp32_peak / 1e12,
+                "unit": "T lane-instr/s", "frac": fp32_achieved / fp32_peak,
+                "peak_kind": "microbenchmark (profiles/r01_microbench_peaks.json)"}
         # kernels of this repo per model step: stage 1 bin_cells, scan_bins,
         # place_ids, reorder_cells, sweep_cubes, predictor_step; stage 2 the
         # same minus bin_cells (fused into the predictor), corrector_step

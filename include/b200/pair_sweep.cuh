@@ -131,6 +131,12 @@ __device__ __forceinline__ void bulk_g2s(
         : "memory");
 }
 
+// Entries in a thread's list column, from the address of its next free entry.
+__device__ __forceinline__ int listed_at(uint32_t next_entry, uint32_t column)
+{
+    return int(next_entry - column) / int(SWEEP_THREADS * sizeof(uint16_t));
+}
+
 // Offset (in cube ids) of neighbour row r = 0..8 relative to a cell's cube.
 // Same ordering as the reference's d_nhood table (solvers.cuh:472-484): the
 // y-shift cycles 0, -1, +1 fastest, the z-shift 0, -1, +1 slowest; inside a row
@@ -445,43 +451,53 @@ __global__ void __launch_bounds__(
             mbar_wait(&s_bar, parity);
             parity ^= 1u;
 
-            // -- phase 1 (scan) and phase 2 (interact). The scan is branch free:
-            //    a hit is stored if its number falls into [base, base + CAP) and
-            //    counted in any case. One pass unless a list overflows; then the
-            //    scan resumes at the row where it did, with the next base.
-            int r_start = 0, count_start = 0, base = 0;
-            bool pending = owned;
-            while (pending) {
-                int slot = count_start - base;  // number of the next hit - base
-                uint16_t* lp = s_list + (slot * SWEEP_THREADS + t);
-                pending = false;
-                for (int r = r_start; r < SWEEP_ROWS; r++) {
-                    const uint32_t range = s_range[r * SWEEP_THREADS + t];
-                    const uint32_t tag = uint32_t(r) << 12;
-                    // the list entry doubles as loop counter
-                    uint32_t entry = tag | (range & 0xffffu);
-                    const uint32_t entry_end = tag | (range >> 16);
-                    const float4* pp = s_pos + (range & 0xffffu);
-                    const int slot_at_row = slot;
+            // -- phase 1 (scan) and phase 2 (interact). The lanes of a warp
+            //    walk the 9 rows together (cells that are not subjects have
+            //    empty ranges). A lane stops scanning when its list is full;
+            //    if any lane of the warp could not finish its row, the whole
+            //    warp interacts with what is listed and resumes where it
+            //    stopped, so the order of the pairs never changes.
+            const uint32_t list_begin = smem_u32(s_list + t);
+            const uint32_t list_full =
+                list_begin + SWEEP_LIST_CAP * SWEEP_THREADS * sizeof(uint16_t);
+            int r = 0;
+            uint32_t range = owned ? s_range[t] : 0u;
+            int a = int(range & 0xffffu), b = int(range >> 16);
+            while (true) {
+                // shared-memory address of the next free entry of this thread's
+                // list column (a plain 32-bit register: one add per hit)
+                uint32_t la = list_begin;
+                while (true) {
+                    const float4* pp = s_pos + a;
+                    // the list entry (row << 12 | position) is the loop counter
+                    uint32_t entry = (uint32_t(r) << 12) | uint32_t(a);
+                    const uint32_t entry_end = entry + uint32_t(b - a);
 #pragma unroll 2
-                    for (; entry < entry_end; entry++, pp++) {
+                    for (; entry < entry_end && la != list_full; entry++, pp++) {
                         const float4 p = *pp;
                         const float dx = me.x - p.x, dy = me.y - p.y,
                                     dz = me.z - p.z;
                         const float d2 = dx * dx + dy * dy + dz * dz;
-                        const bool hit = !(d2 > reach2);
-                        if (hit && unsigned(slot) < unsigned(SWEEP_LIST_CAP))
-                            *lp = uint16_t(entry);
-                        if (hit) slot++, lp += SWEEP_THREADS;
+                        if (!(d2 > reach2)) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(la),
+                                         "h"(uint16_t(entry))
+                                         : "memory");
+                            la += SWEEP_THREADS * sizeof(uint16_t);
+                        }
                     }
-                    if (slot > SWEEP_LIST_CAP) {
-                        pending = true;
-                        r_start = r, count_start = base + slot_at_row;
-                        break;
-                    }
+                    a = int(entry & 4095u);
+                    if (__any_sync(0xffffffffu, a < b)) break;  // list(s) full
+                    // (the next range is fetched before the exit test on
+                    // purpose: with the test first, ptxas 12.9 replaces r in
+                    // the address by the exit value and reads row 9)
+                    ++r;
+                    range = owned && r < SWEEP_ROWS
+                                ? s_range[r * SWEEP_THREADS + t]
+                                : 0u;
+                    a = int(range & 0xffffu), b = int(range >> 16);
+                    if (r == SWEEP_ROWS) break;
                 }
-                const int listed = min(max(slot, 0), SWEEP_LIST_CAP);
-                base += SWEEP_LIST_CAP;
+                const int listed = listed_at(la, list_begin);
 
                 for (int e = 0; e < listed; e++) {
                     const unsigned entry = s_list[e * SWEEP_THREADS + t];
@@ -502,6 +518,7 @@ __global__ void __launch_bounds__(
                     sum_friction += friction;
                     if (friction != 0.f) sum_v += friction * vj;
                 }
+                if (r == SWEEP_ROWS) break;
             }
         }
 
