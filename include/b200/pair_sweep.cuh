@@ -61,11 +61,22 @@ namespace yb {
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_ROWS = 9;
 
+#ifndef YB_SWEEP_HEAVY_STAGE  // tuning overrides (profiles/r01_sweep_tuning.md)
+#define YB_SWEEP_HEAVY_STAGE 1280
+#endif
+#ifndef YB_SWEEP_HEAVY_LIST
+#define YB_SWEEP_HEAVY_LIST 24
+#endif
+#ifndef YB_SWEEP_HEAVY_CTAS
+#define YB_SWEEP_HEAVY_CTAS 6
+#endif
+
 template<int LANES>
 struct Sweep_config {
-    static constexpr int stage_cap = LANES <= 4 ? 1024 : 1280;  // <= 4095
-    static constexpr int list_cap = 24;
-    static constexpr int min_ctas = LANES <= 4 ? 8 : 6;
+    static constexpr int stage_cap =
+        LANES <= 4 ? 1024 : YB_SWEEP_HEAVY_STAGE;  // <= 4095
+    static constexpr int list_cap = LANES <= 4 ? 24 : YB_SWEEP_HEAVY_LIST;
+    static constexpr int min_ctas = LANES <= 4 ? 8 : YB_SWEEP_HEAVY_CTAS;
     static constexpr size_t smem =
         size_t(stage_cap) * sizeof(float4) +
         size_t(SWEEP_ROWS) * SWEEP_THREADS * sizeof(uint32_t) +

@@ -253,3 +253,8 @@ void regular_rectangle(float dist_to_nb, int nx, Solution<Pt, Solver>& points,
     }
     points.copy_to_device();
 }
+
+
+// Extension: the same distributions from a counter-based generator, generated
+// and relaxed on the device (seeded_sphere, relaxed_seeded_sphere, ...).
+#include "b200/seeded_inits.cuh"

@@ -92,6 +92,16 @@ int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity);
 int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n);
 int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity);
 
+/* Extension (product library only; YB_ENOSYS elsewhere): fill the model with
+ * n cells of a seeded uniform ball at neighbour distance dist_to_nb, generated
+ * on the device (b200/seeded_inits.cuh; radius formula of random_sphere,
+ * inits.cuh:41-48), extra lanes and old velocities zero. With relax_steps != 0
+ * the ball is generated at distance 0.6, relaxed with that many relu_force
+ * steps (< 0: the reference's step count, inits.cuh:96-112) and rescaled like
+ * relaxed_sphere. float3 Grid/Tile models only. */
+int yb_sim_seed_sphere(yb_sim* sim, int n, float dist_to_nb,
+    unsigned long long seed, int relax_steps);
+
 /* Links of models that have them: pairs (a, b) as 2 * n_links ints. */
 int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links);
 

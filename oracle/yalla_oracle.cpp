@@ -934,6 +934,11 @@ int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity)
 {
     return sim->get_ints(name, h_values, capacity);
 }
+int yb_sim_seed_sphere(yb_sim*, int, float, unsigned long long, int)
+{
+    return fail(YB_ENOSYS, "seeded device generators exist in the product library only");
+}
+
 int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links)
 {
     return sim->set_links(h_links, n_links);

@@ -369,6 +369,66 @@ def test_growth_appended_cells_are_integrated(product):
 
 
 # ---- full-size properties (the benchmark configuration) ----------------------------------
+# ---- seeded device-side initial conditions (extension, b200/seeded_inits.cuh) ----------
+def test_seeded_sphere_distribution_and_determinism(product):
+    n, d = 200_000, 0.8
+    states = []
+    for seed in (7, 7, 8):
+        with product.sim("relu_grid", n, 100, 1.0) as sim:
+            sim.seed_sphere(n, d, seed)
+            assert sim.n() == n
+            states.append(sim.get_state())
+    assert np.array_equal(states[0], states[1])       # the seed is the tissue
+    assert not np.array_equal(states[0], states[2])
+    X = states[0].astype(np.float64)
+    radius = workloads.ball_radius(n, d)              # inits.cuh:41-48
+    r = np.linalg.norm(X, axis=1)
+    assert r.max() <= radius * (1 + 1e-5)
+    # uniform in the ball: r^3 uniform, directions isotropic
+    counts, _ = np.histogram((r / radius) ** 3, bins=10, range=(0, 1))
+    assert np.all(np.abs(counts - n / 10) < 5 * np.sqrt(n / 10))
+    assert np.all(np.abs(X.mean(axis=0)) < 5 * radius / np.sqrt(3 * n))
+    octant = (X > 0).astype(int) @ np.array([1, 2, 4])
+    assert np.all(np.abs(np.bincount(octant, minlength=8) - n / 8)
+                  < 5 * np.sqrt(n / 8))
+
+
+def test_seeded_sphere_prefix_is_independent_of_n(product):
+    # counter-based generator keyed by (seed, cell): cell i gets the same
+    # uniforms however many cells are generated; only the radius scales
+    out = []
+    for n in (1000, 5000):
+        with product.sim("relu_grid", 5000, 50, 1.0) as sim:
+            sim.seed_sphere(n, 0.8, 3)
+            out.append(sim.get_state())
+    scale = (1000 / 5000) ** (1.0 / 3.0)
+    assert np.allclose(out[0], out[1][:1000] * scale, rtol=1e-5, atol=1e-6)
+
+
+def test_relaxed_seeded_sphere(product):
+    from scipy.spatial import cKDTree
+    n, d = 2000, 0.75
+    with product.sim("relu_grid", n, 50, 1.0) as sim:
+        sim.seed_sphere(n, d, 11, relax_steps=-1)  # the reference's 2000 steps
+        X = sim.get_state().astype(np.float64)
+        assert sim.n() == n
+    assert np.all(np.isfinite(X))
+    nearest = cKDTree(X).query(X, k=2)[0][:, 1]
+    # relaxed: nobody much closer than the equilibrium distance, and the mean
+    # nearest-neighbour distance close to it (relu_force, inits.cuh:78-93)
+    assert nearest.min() > 0.6 * d
+    assert abs(np.median(nearest) - d) < 0.12 * d
+    with product.sim("relu_grid", n, 50, 1.0) as sim:
+        sim.seed_sphere(n, d, 11, relax_steps=-1)
+        assert np.array_equal(sim.get_state().astype(np.float64), X)
+
+
+def test_seeded_sphere_needs_the_product_library(oracle):
+    with oracle.sim("relu_grid", 100, 20, 1.0) as sim:
+        with pytest.raises(Exception):
+            sim.seed_sphere(100, 0.8, 1)
+
+
 @pytest.fixture(scope="module")
 def million():
     n = 1_000_000

@@ -50,6 +50,9 @@ SIGNATURES = {
                                        ctypes.c_void_p, ctypes.c_int]),
     "yb_sim_get_ints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
                                        ctypes.c_void_p, ctypes.c_int]),
+    "yb_sim_seed_sphere": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_float, ctypes.c_ulonglong,
+                                          ctypes.c_int]),
     "yb_sim_set_links": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_int]),
     "yb_sim_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
@@ -255,6 +258,11 @@ class Sim:
             self.handle, name.encode(), out.ctypes.data, self.n_max),
             f"get_ints({name})")
         return out[:self.n()].copy()
+
+    def seed_sphere(self, n, dist_to_nb, seed, relax_steps=0):
+        """Seeded ball generated (and optionally relaxed) on the device."""
+        self.lib.check(self.lib.cdll.yb_sim_seed_sphere(
+            self.handle, n, dist_to_nb, seed, relax_steps), "seed_sphere")
 
     def set_links(self, links):
         links = _i32(links).reshape(-1, 2)

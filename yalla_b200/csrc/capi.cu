@@ -56,6 +56,10 @@ struct yb_sim {
     {
         return fail(YB_EINVAL, "model has no int property " + name);
     }
+    virtual int seed_sphere(int, float, unsigned long long, int)
+    {
+        return fail(YB_ENOSYS, "seeded generators: float3 models of the product library");
+    }
     virtual int set_links(const int* h_links, int n_links)
     {
         return fail(YB_EINVAL, "model has no links");
@@ -403,6 +407,21 @@ struct Spring_sim : Sim_base<float3, Solver> {
         return 0;
     }
 #ifdef YALLA_B200
+    int seed_sphere(int n, float dist_to_nb, unsigned long long seed,
+        int relax_steps) override
+    {
+        if (n <= 0 || n > this->cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        *this->cells.h_n = n;
+        cudaMemsetAsync(this->cells.d_old_v, 0,
+            sizeof(float3) * static_cast<size_t>(this->cells.n_max),
+            this->cells.stream);
+        if (relax_steps == 0)
+            seeded_sphere(dist_to_nb, this->cells, seed);
+        else
+            relaxed_seeded_sphere(dist_to_nb, this->cells, seed, 0, relax_steps);
+        this->n_host = n;
+        return check_cuda("yb_sim_seed_sphere");
+    }
     int dd_forces(int stage, float* sums4) override
     {
         // only the grid solver knows ghosts; the Tile solver is replicas-only
@@ -803,6 +822,12 @@ int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n)
 int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity)
 {
     return sim->get_ints(name, h_values, capacity);
+}
+
+int yb_sim_seed_sphere(yb_sim* sim, int n, float dist_to_nb,
+    unsigned long long seed, int relax_steps)
+{
+    return sim->seed_sphere(n, dist_to_nb, seed, relax_steps);
 }
 
 int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links)
