@@ -339,3 +339,8 @@ void Vtk_input::read_property(Property<Prop>& property, std::string prop_name)
         std::istringstream(line) >> property.h_prop[i];
     }
 }
+
+
+// Extension: Vtk_async_output<Pt>, snapshots on the solver's stream and writes
+// frames (ASCII or binary) from a background thread.
+#include "b200/vtk_async.cuh"

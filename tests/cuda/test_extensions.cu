@@ -1,0 +1,116 @@
+// GPU test program for header-level extensions that have no C-ABI entry:
+// Vtk_async_output against the synchronous Vtk_output, and the seeded
+// generators through the header API. Prints one "ok <name>" line per check
+// and exits non-zero on the first failure (run by tests/test_extensions_gpu.py).
+#include <stdio.h>
+#include <stdlib.h>
+#include <fstream>
+#include <iterator>
+#include <string>
+
+#include "../../include/dtypes.cuh"
+#include "../../include/inits.cuh"
+#include "../../include/polarity.cuh"
+#include "../../include/solvers.cuh"
+#include "../../include/vtk.cuh"
+
+#define CHECK(cond, name)                                   \
+    do {                                                    \
+        if (!(cond)) {                                      \
+            printf("FAILED %s (%s:%d)\n", name, __FILE__, __LINE__); \
+            exit(1);                                        \
+        }                                                   \
+        printf("ok %s\n", name);                            \
+    } while (0)
+
+static std::string slurp(const std::string& path)
+{
+    std::ifstream file(path, std::ios::binary);
+    return std::string(
+        std::istreambuf_iterator<char>(file), std::istreambuf_iterator<char>());
+}
+
+__device__ Po_cell layer(Po_cell Xi, Po_cell r, float dist, int i, int j)
+{
+    Po_cell dF{0};
+    if (i == j or dist > 1) return dF;
+    const float F = fmaxf(0.7f - dist, 0.f) * 2.f - fmaxf(dist - 0.8f, 0.f);
+    dF.x = r.x * F / dist, dF.y = r.y * F / dist, dF.z = r.z * F / dist;
+    dF += bending_force(Xi, r, dist) * 0.2f;
+    return dF;
+}
+
+int main(int argc, char** argv)
+{
+    const std::string dir = argc > 1 ? argv[1] : "/tmp/yb_ext_test/";
+    const int n = 3000, n_max = 4000;
+
+    // ---- seeded generators through the header API ------------------------
+    Solution<Po_cell, Grid_solver> cells{n_max, 50, 1.f};
+    *cells.h_n = n;
+    for (int i = 0; i < n_max; i++) cells.h_X[i] = Po_cell{0};
+    cells.copy_to_device();
+    seeded_sphere(0.8f, cells, 42);
+    CHECK(*cells.h_n == n && cells.get_d_n() == n, "seeded_sphere keeps n");
+    float r_max = 0;
+    for (int i = 0; i < n; i++) {
+        const Po_cell& X = cells.h_X[i];
+        r_max = fmaxf(r_max, sqrtf(X.x * X.x + X.y * X.y + X.z * X.z));
+        cells.h_X[i].theta = acosf(X.z / fmaxf(1e-6f, sqrtf(X.x * X.x + X.y * X.y + X.z * X.z)));
+        cells.h_X[i].phi = atan2f(X.y, X.x);
+    }
+    const float radius = powf(n / 0.64f, 1.f / 3) * 0.8f / 2;
+    CHECK(r_max <= radius * 1.00001f && r_max > 0.9f * radius,
+        "seeded_sphere radius");
+    cells.copy_to_device();
+
+    // ---- frames: synchronous ASCII writer vs asynchronous ASCII writer -----
+    {
+        // same base name (it is part of the file header), different folders
+        Vtk_output sync_out{"frame", dir + "sync/", false};
+        Vtk_async_output<Po_cell> async_out{n_max, "frame", dir + "async/", false};
+        async_out.add_field("theta", &Po_cell::theta);
+        async_out.add_polarity(&Po_cell::theta, &Po_cell::phi);
+        Vtk_async_output<Po_cell> binary_out{n_max, "binary", dir, true, 3};
+        binary_out.add_field("theta", &Po_cell::theta);
+        for (int frame = 0; frame < 4; frame++) {
+            async_out.write(cells);   // returns at once
+            binary_out.write(cells);
+            cells.copy_to_host();     // the reference's blocking path
+            sync_out.write_positions(cells);
+            sync_out.write_field(cells, "theta", &Po_cell::theta);
+            sync_out.write_polarity(cells);
+            for (int k = 0; k < 5; k++) cells.take_step<layer>(0.05f);
+        }
+        async_out.wait();
+        binary_out.wait();
+        CHECK(async_out.frames_written() == 4, "async frames written");
+        bool same = true;
+        for (int frame = 0; frame < 4; frame++) {
+            const std::string a =
+                slurp(dir + "sync/frame_" + std::to_string(frame) + ".vtk");
+            const std::string b = slurp(async_out.frame_path(frame));
+            same = same && !a.empty() && a == b;
+        }
+        CHECK(same, "async ASCII frames identical to Vtk_output");
+        const std::string first = slurp(binary_out.frame_path(3));
+        CHECK(first.find("BINARY") != std::string::npos &&
+                  first.size() > size_t(n) * 12,
+            "binary frame written");
+    }
+
+    // ---- a growing tissue: the frame holds the device-side count -----------
+    {
+        Vtk_async_output<Po_cell> out{n_max, "grown", dir, false};
+        const int more = n + 100;
+        cudaMemcpy(cells.d_n, &more, sizeof(int), cudaMemcpyHostToDevice);
+        out.write(cells);
+        out.wait();
+        const std::string text = slurp(out.frame_path(0));
+        CHECK(text.find("POINTS " + std::to_string(more) + " float") !=
+                  std::string::npos,
+            "frame uses the device-side cell count");
+    }
+    printf("all extension checks passed\n");
+    return 0;
+}

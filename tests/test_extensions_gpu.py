@@ -1,0 +1,22 @@
+"""Header-level extensions without a C-ABI entry, exercised by the CUDA test
+programs in tests/cuda/ (built into tests/_bin/ by yalla_b200/build.py):
+Vtk_async_output -- asynchronous frames identical to Vtk_output's -- and the
+seeded generators through the header API."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_extension_programs(tmp_path):
+    binary = os.path.join(ROOT, "tests", "_bin", "test_extensions")
+    assert os.path.exists(binary), "run __graft_entry__.build() first"
+    result = subprocess.run([binary, str(tmp_path) + "/"], capture_output=True,
+                            text=True, timeout=600)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    assert "all extension checks passed" in result.stdout
+    assert result.stdout.count("ok ") >= 6

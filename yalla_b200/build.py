@@ -55,5 +55,25 @@ def build_product(force=False):
     return out
 
 
+def build_extension_tests(force=False):
+    """tests/cuda/*.cu -- GPU test programs for header-level extensions that
+    have no C-ABI entry -- into tests/_bin/ (run by tests/test_extensions_gpu.py)."""
+    out_dir = os.path.join(ROOT, "tests", "_bin")
+    os.makedirs(out_dir, exist_ok=True)
+    built = []
+    source_dir = os.path.join(ROOT, "tests", "cuda")
+    for name in sorted(os.listdir(source_dir)):
+        if not name.endswith(".cu"):
+            continue
+        source = os.path.join(source_dir, name)
+        out = os.path.join(out_dir, name[:-3])
+        if force or not _newer(out, [os.path.join(ROOT, "include"), source]):
+            _run(["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"),
+                 "-o", out, source])
+        built.append(out)
+    return built
+
+
 if __name__ == "__main__":
     print(build_product(force=True))
+    print(build_extension_tests(force=True))
