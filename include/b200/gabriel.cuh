@@ -172,7 +172,8 @@ protected:
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
         bool binned_by_predictor, cudaEvent_t before_sweep = nullptr)
     {
-        this->build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
+        if (!this->take_index_ahead())
+            this->build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
         const int ctas = this->persistent_ctas(
             prepare<pw_int, pw_friction, SEEDED>(), yb::GABRIEL_THREADS, max_ctas);
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));

@@ -265,6 +265,7 @@ public:
         YB_CUDA(cudaStreamCreateWithFlags(
             &capture_stream, cudaStreamNonBlocking));
         YB_CUDA(cudaMallocHost(&h_n_pinned, sizeof(int)));
+        YB_CUDA(cudaEventCreateWithFlags(&count_ready, cudaEventDisableTiming));
     }
     Heun_solver(const Heun_solver&) = delete;
     Heun_solver& operator=(const Heun_solver&) = delete;
@@ -274,6 +275,7 @@ public:
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         if (slab.capacity > 0) slab.release();
         cudaFreeHost(h_n_pinned);
+        cudaEventDestroy(count_ready);
         cudaStreamDestroy(capture_stream);
         cudaFree(d_partials);
         cudaFree(d_ctl);
@@ -521,9 +523,19 @@ protected:
         const int mode1 = fix_com ? yb::DRIFT_MEAN : yb::DRIFT_POINT;
 
         if (!yb::is_no_gen_forces(gen_forces)) {
-            // The callback is arbitrary host code that needs n: one blocking
-            // read of d_n, then the stage kernels are issued directly.
-            const int n = get_d_n();
+            // The callback is arbitrary host code that needs n: one read of
+            // d_n per step, then the stage kernels are issued directly. The
+            // read goes through a side stream while the grid build of the first stage
+            // (which needs neither n on the host nor the callback's output)
+            // already runs, so the device does not idle during the round trip.
+            YB_CUDA(cudaEventRecord(count_ready, stream));
+            YB_CUDA(cudaStreamWaitEvent(capture_stream, count_ready, 0));
+            YB_CUDA(cudaMemcpyAsync(h_n_pinned, d_n, sizeof(int),
+                cudaMemcpyDeviceToHost, capture_stream));
+            Computer<Pt>::index_ahead(stream, d_n, d_X, d_old_v, d_ctl);
+            YB_CUDA(cudaStreamSynchronize(capture_stream));
+            const int n = *h_n_pinned;
+            assert(n <= n_max);
             enqueue_stage<pw_int, pw_friction, true>(
                 stream, 0, dt, mode0, n, gen_forces);
             enqueue_stage<pw_int, pw_friction, true>(
@@ -575,6 +587,7 @@ private:
     cudaStream_t capture_stream;
     std::vector<yb::Step_graph> graphs;
     int* h_n_pinned = nullptr;
+    cudaEvent_t count_ready = nullptr;
     yb::Slab_scratch slab;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
@@ -640,6 +653,11 @@ public:
 
 protected:
     float graph_key() const { return split_pairs ? 1.f : 0.f; }
+
+    // nothing to prepare ahead of the generic forces
+    void index_ahead(
+        cudaStream_t, const int*, const Pt*, const float3*, yb::Step_ctl*)
+    {}
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
         bool SEEDED>
@@ -933,6 +951,22 @@ protected:
             sort.key, sort.offset, sort.slot_id, pos4, aux, cube_sorted);
     }
 
+    // The first stage's index, built before the generic forces are known (they only
+    // seed dX); the next pwints() call then goes straight to the sweep.
+    void index_ahead(cudaStream_t s, const int* d_n, const Pt* d_X,
+        const float3* d_old_v, yb::Step_ctl* d_ctl)
+    {
+        build_index(s, d_n, d_X, d_old_v, d_ctl, false);
+        indexed_ahead = true;
+    }
+    bool take_index_ahead()
+    {
+        const bool ahead = indexed_ahead;
+        indexed_ahead = false;
+        return ahead;
+    }
+    bool indexed_ahead = false;
+
     int persistent_ctas(int ctas_per_sm, int threads, int max_ctas) const
     {
         int ctas = yb::sm_count() * ctas_per_sm;
@@ -949,7 +983,8 @@ protected:
         int stage, int drift_mode, int fix_point, yb::Step_ctl* d_ctl,
         bool binned_by_predictor, cudaEvent_t before_sweep = nullptr)
     {
-        build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
+        if (!take_index_ahead())
+            build_index(s, d_n, d_X, d_old_v, d_ctl, binned_by_predictor);
         const int ctas = persistent_ctas(
             prepare<pw_int, pw_friction, SEEDED>(), yb::SWEEP_THREADS, max_ctas);
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
