@@ -181,6 +181,54 @@ __device__ __forceinline__ unsigned long long scan_peek(
     return word;
 }
 
+// Decoupled look-back of one warp: publish this tile's aggregate, walk back to
+// the nearest tile that already knows its inclusive prefix, publish ours, and
+// return the exclusive prefix of the tile (valid in every lane).
+__device__ __forceinline__ int scan_lookback(unsigned long long* status,
+    int tile, unsigned epoch, int aggregate, int lane_id)
+{
+    int exclusive = 0;
+    if (tile == 0) {
+        if (lane_id == 0)
+            scan_publish(status, scan_word(epoch, SCAN_PREFIX, aggregate));
+        return 0;
+    }
+    if (lane_id == 0)
+        scan_publish(status + tile, scan_word(epoch, SCAN_AGGREGATE, aggregate));
+    int look = tile - 1;  // lane 0 inspects `look`, lane l `look - l`
+    while (true) {
+        const int mine = look - lane_id;
+        unsigned state = SCAN_PREFIX;
+        int value = 0;
+        if (mine >= 0) {
+            unsigned long long word;
+            do {
+                word = scan_peek(status + mine);
+                state = static_cast<unsigned>(word >> 32);
+            } while ((state >> 2) != epoch || (state & 3u) == 0u);
+            state &= 3u;
+            value = static_cast<int>(static_cast<unsigned>(word));
+        }
+        // nearest predecessor that already knows its inclusive prefix
+        const unsigned has_prefix =
+            __ballot_sync(0xffffffffu, state == SCAN_PREFIX);
+        // lanes up to and including it contribute; the whole window does if
+        // nobody in it has a prefix yet
+        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
+        int contrib = (lane_id <= stop && mine >= 0) ? value : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        exclusive += contrib;
+        if (has_prefix != 0u) break;
+        look -= 32;
+    }
+    if (lane_id == 0)
+        scan_publish(
+            status + tile, scan_word(epoch, SCAN_PREFIX, exclusive + aggregate));
+    return exclusive;
+}
+
 // count: padded to scan_padded(n_entries), zero beyond n_entries; zeroed again
 // on exit. offset: same padding; offset[c] = sum of count[0..c).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_bins(int* count,
@@ -236,46 +284,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_bins(int* count,
     const int aggregate = running;
 
     if (warp_id == 0) {
-        int exclusive = 0;
-        if (tile == 0) {
-            if (lane_id == 0)
-                scan_publish(status, scan_word(epoch, SCAN_PREFIX, aggregate));
-        } else {
-            if (lane_id == 0)
-                scan_publish(status + tile,
-                    scan_word(epoch, SCAN_AGGREGATE, aggregate));
-            int look = tile - 1;  // lane 0 inspects `look`, lane l `look - l`
-            while (true) {
-                const int mine = look - lane_id;
-                unsigned state = SCAN_PREFIX;
-                int value = 0;
-                if (mine >= 0) {
-                    unsigned long long word;
-                    do {
-                        word = scan_peek(status + mine);
-                        state = static_cast<unsigned>(word >> 32);
-                    } while ((state >> 2) != epoch || (state & 3u) == 0u);
-                    state &= 3u;
-                    value = static_cast<int>(static_cast<unsigned>(word));
-                }
-                // nearest predecessor that already knows its inclusive prefix
-                const unsigned has_prefix =
-                    __ballot_sync(0xffffffffu, state == SCAN_PREFIX);
-                // lanes up to and including it contribute; the whole window
-                // does if nobody in it has a prefix yet
-                const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
-                int contrib = (lane_id <= stop && mine >= 0) ? value : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1)
-                    contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                exclusive += contrib;
-                if (has_prefix != 0u) break;
-                look -= 32;
-            }
-            if (lane_id == 0)
-                scan_publish(status + tile,
-                    scan_word(epoch, SCAN_PREFIX, exclusive + aggregate));
-        }
+        const int exclusive =
+            scan_lookback(status, tile, epoch, aggregate, lane_id);
         if (lane_id == 0) s_tile_prefix = exclusive;
     }
     __syncthreads();

@@ -10,7 +10,7 @@
 //   always sent at full capacity (NVLink makes that cheaper than a host round
 //   trip for the count); the receiver reads the count from the header.
 //
-// Packing is a stable stream compaction (flags -> scan_bins -> scatter), so the
+// Packing is a stable single-pass stream compaction (slab_select), so the
 // order of ghosts and migrants, and with it every floating-point sum on the
 // receiving side, is reproducible.
 #pragma once
@@ -23,27 +23,6 @@
 namespace yb {
 
 constexpr int SLAB_HEADER = 4;  // floats in front of the records
-
-// Which owned cells go to the lower / upper neighbour. Halo: lo_edge = z_lo +
-// halo, hi_edge = z_hi - halo (a cell may go both ways in a thin slab).
-// Migration: lo_edge = z_lo, hi_edge = z_hi, and `stay` marks the rest.
-template<typename Pt>
-__global__ void __launch_bounds__(256) slab_flags(const Step_ctl* ctl,
-    const Pt* __restrict__ P, float lo_edge, float hi_edge, int has_lower,
-    int has_upper, int* __restrict__ flag_lo, int* __restrict__ flag_hi,
-    int* __restrict__ flag_stay)
-{
-    const int n = ctl->n_owned;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += gridDim.x * blockDim.x) {
-        const float z = __ldg(reinterpret_cast<const float*>(P + i) + 2);
-        const int lo = has_lower && z < lo_edge;
-        const int hi = has_upper && z >= hi_edge;
-        flag_lo[i] = lo;
-        flag_hi[i] = hi;
-        if (flag_stay) flag_stay[i] = !(lo || hi);
-    }
-}
 
 template<typename Pt>
 __device__ __forceinline__ void write_record(
@@ -73,29 +52,137 @@ __device__ __forceinline__ void read_record(
     w[2] = record[L::lanes + 2];
 }
 
-// off_*: exclusive scans of the flags (n + 1 valid entries). Cells whose flag
-// was set are those with off[i + 1] != off[i].
+// Which owned cells go to the lower / upper neighbour, and where: a
+// single-pass stable stream compaction with
+// decoupled look-back (grid_build.cuh) over tiles of SCAN_TILE cells. Every
+// tile counts its cells bound for the lower and for the upper neighbour, warps
+// 0 and 1 resolve the two running prefixes at the same time, and the tile then
+// writes its records straight to their final positions. In a migration round
+// every cell goes exactly one way, so the rank of a cell that stays is its
+// index minus the cells before it that leave: the stayers are compacted in the
+// same pass. The order of records is ascending cell index, exactly as with the
+// separate passes.
+constexpr int SELECT_SUB = SCAN_TILE / SCAN_THREADS;  // cells per thread
+
 template<typename Pt>
-__global__ void __launch_bounds__(256) slab_pack(Step_ctl* ctl,
-    const Pt* __restrict__ P, const float3* __restrict__ v,
-    const int* __restrict__ off_lo, const int* __restrict__ off_hi,
-    float* __restrict__ send_lo, float* __restrict__ send_hi, int capacity)
+__global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
+    Step_ctl* scan_ctl, const Pt* __restrict__ P, const float3* __restrict__ v,
+    float lo_edge, float hi_edge, int has_lower, int has_upper, int migration,
+    float* __restrict__ send_lo, float* __restrict__ send_hi, int capacity,
+    Pt* __restrict__ X_tmp, float3* __restrict__ v_tmp, int* n_stay,
+    unsigned long long* status_lo, unsigned long long* status_hi, int n_tiles)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
+    constexpr int WARPS = SCAN_THREADS / 32;
+    __shared__ int s_tile;
+    __shared__ int s_count[2][SELECT_SUB][WARPS];  // then: exclusive prefixes
+    __shared__ int s_total[2];
+    __shared__ int s_tile_prefix[2];
+
+    const int t = threadIdx.x;
+    const int lane_id = t & 31, warp_id = t >> 5;
+    if (t == 0) s_tile = atomicAdd(&scan_ctl->scan_next_tile, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const unsigned epoch =
+        static_cast<unsigned>(*(volatile int*)&scan_ctl->scan_epoch) & 0x3fffffffu;
     const int n = ctl->n_owned;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += gridDim.x * blockDim.x) {
-        const int a = off_lo[i], b = off_hi[i];
-        if (off_lo[i + 1] != a && a < capacity)
-            write_record(send_lo + SLAB_HEADER + size_t(a) * W, P, v, i);
-        if (off_hi[i + 1] != b && b < capacity)
-            write_record(send_hi + SLAB_HEADER + size_t(b) * W, P, v, i);
+    const int first = tile * SCAN_TILE;
+
+    // sub-block u holds cells first + u * THREADS + t: coalesced, and ranks in
+    // (u, warp, lane) order are ranks in cell order
+    unsigned flags = 0;  // bit 2u: goes down, bit 2u + 1: goes up
+#pragma unroll
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int i = first + u * SCAN_THREADS + t;
+        int lo = 0, hi = 0;
+        if (i < n) {
+            const float z = __ldg(reinterpret_cast<const float*>(P + i) + 2);
+            lo = has_lower && z < lo_edge;
+            hi = has_upper && z >= hi_edge;
+        }
+        flags |= (unsigned(lo) << (2 * u)) | (unsigned(hi) << (2 * u + 1));
+        const unsigned lo_mask = __ballot_sync(0xffffffffu, lo);
+        const unsigned hi_mask = __ballot_sync(0xffffffffu, hi);
+        if (lane_id == 0) {
+            s_count[0][u][warp_id] = __popc(lo_mask);
+            s_count[1][u][warp_id] = __popc(hi_mask);
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int n_lo = off_lo[n], n_hi = off_hi[n];
-        if (n_lo > capacity || n_hi > capacity) atomicAdd(&ctl->out_of_grid, 1 << 20);
+    __syncthreads();
+    // exclusive scan of the SUB x WARPS counts, one warp per direction
+    if (warp_id < 2) {
+        constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
+        int* counts = &s_count[warp_id][0][0];
+        int mine[PER_LANE], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            mine[q] = counts[lane_id * PER_LANE + q];
+            sum += mine[q];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_id >= d) incl += up;
+        }
+        int running = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            counts[lane_id * PER_LANE + q] = running;
+            running += mine[q];
+        }
+        const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
+        const int exclusive = scan_lookback(warp_id == 0 ? status_lo : status_hi,
+            tile, epoch, aggregate, lane_id);
+        if (lane_id == 0) {
+            s_total[warp_id] = aggregate;
+            s_tile_prefix[warp_id] = exclusive;
+        }
+    }
+    __syncthreads();
+    const int prefix_lo = s_tile_prefix[0], prefix_hi = s_tile_prefix[1];
+
+#pragma unroll
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int i = first + u * SCAN_THREADS + t;
+        const int lo = (flags >> (2 * u)) & 1, hi = (flags >> (2 * u + 1)) & 1;
+        const unsigned lo_mask = __ballot_sync(0xffffffffu, lo);
+        const unsigned hi_mask = __ballot_sync(0xffffffffu, hi);
+        const unsigned below = (1u << lane_id) - 1u;
+        const int a = prefix_lo + s_count[0][u][warp_id] + __popc(lo_mask & below);
+        const int b = prefix_hi + s_count[1][u][warp_id] + __popc(hi_mask & below);
+        if (i >= n) continue;
+        if (lo && a < capacity)
+            write_record(send_lo + SLAB_HEADER + size_t(a) * W, P, v, i);
+        if (hi && b < capacity)
+            write_record(send_hi + SLAB_HEADER + size_t(b) * W, P, v, i);
+        if (migration && !lo && !hi) {
+            const int to = i - a - b;
+            store_pt(X_tmp, to, load_pt(P, i));
+            v_tmp[to] = v[i];
+        }
+    }
+
+    // the tile that holds the last owned cell knows the totals
+    const int last_tile = n > 0 ? (n - 1) / SCAN_TILE : 0;
+    if (t == 0 && tile == last_tile) {
+        const int n_lo = prefix_lo + s_total[0], n_hi = prefix_hi + s_total[1];
+        if (n_lo > capacity || n_hi > capacity)
+            atomicAdd(&ctl->out_of_grid, 1 << 20);
         send_lo[0] = __int_as_float(min(n_lo, capacity));
         send_hi[0] = __int_as_float(min(n_hi, capacity));
+        if (migration) *n_stay = n - n_lo - n_hi;
+    }
+    // The last tile to finish re-arms the control words for the next launch.
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(&scan_ctl->scan_tiles_done, 1) == n_tiles - 1) {
+            scan_ctl->scan_next_tile = 0;
+            scan_ctl->scan_tiles_done = 0;
+            scan_ctl->scan_epoch = static_cast<int>((epoch + 1u) & 0x3fffffffu);
+            __threadfence();
+        }
     }
 }
 
@@ -123,33 +210,16 @@ __global__ void __launch_bounds__(256) slab_append_ghosts(Step_ctl* ctl,
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_n = n + n_lo + n_hi;
 }
 
-// Migration, step 1: stable compaction of the cells that stay into scratch.
-template<typename Pt>
-__global__ void __launch_bounds__(256) slab_compact_stayers(const Step_ctl* ctl,
-    const Pt* __restrict__ X, const float3* __restrict__ v,
-    const int* __restrict__ off_stay, Pt* __restrict__ X_tmp,
-    float3* __restrict__ v_tmp)
-{
-    const int n = ctl->n_owned;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += gridDim.x * blockDim.x) {
-        const int to = off_stay[i];
-        if (off_stay[i + 1] == to) continue;
-        store_pt(X_tmp, to, load_pt(X, i));
-        v_tmp[to] = v[i];
-    }
-}
-
 // Migration, step 2: owned cells := stayers, arrivals from below, from above.
 template<typename Pt>
 __global__ void __launch_bounds__(256) slab_merge(const Step_ctl* ctl,
-    const int* __restrict__ off_stay, const Pt* __restrict__ X_tmp,
+    const int* __restrict__ n_stay_in, const Pt* __restrict__ X_tmp,
     const float3* __restrict__ v_tmp, const float* __restrict__ recv_lo,
     const float* __restrict__ recv_hi, int has_lower, int has_upper, int n_max,
     Pt* X, float3* v, int* new_count)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
-    const int n_stay = off_stay[ctl->n_owned];
+    const int n_stay = *n_stay_in;
     int n_lo = has_lower ? __float_as_int(recv_lo[0]) : 0;
     int n_hi = has_upper ? __float_as_int(recv_hi[0]) : 0;
     n_lo = max(0, min(n_lo, n_max - n_stay));
@@ -187,45 +257,38 @@ __global__ void slab_set_drift(Step_ctl* ctl, int stage, const float* sums4)
     ctl->drift[stage][2] = sums4[2] * inv_n;
 }
 
-// Scratch of the compactions: three flag arrays and their scans.
+// Scratch of the compaction: look-back status words of both directions.
 struct Slab_scratch {
     int capacity = 0;     // records per exchange buffer
-    int n_tiles = 0;      // scan tiles covering n_max + 1 entries
-    int* flag[3] = {nullptr, nullptr, nullptr};
-    int* off[3] = {nullptr, nullptr, nullptr};
-    unsigned long long* status = nullptr;
+    int n_tiles = 0;      // tiles of SCAN_TILE cells covering n_max
+    unsigned long long* status[2] = {nullptr, nullptr};
     Step_ctl* scan_ctl = nullptr;  // scan bookkeeping only
+    int* n_stay = nullptr;
     int* new_count = nullptr;
     float z_lo = 0.f, z_hi = 0.f, halo = 0.f;
     int has_lower = 0, has_upper = 0;
 
     void allocate(int n_max)
     {
-        const size_t bins = static_cast<size_t>(scan_padded(n_max + 1));
-        n_tiles = static_cast<int>(bins / SCAN_TILE);
-        for (int k = 0; k < 3; k++) {
-            YB_CUDA(cudaMalloc(&flag[k], bins * sizeof(int)));
-            YB_CUDA(cudaMemset(flag[k], 0, bins * sizeof(int)));
-            YB_CUDA(cudaMalloc(&off[k], bins * sizeof(int)));
-            YB_CUDA(cudaMemset(off[k], 0, bins * sizeof(int)));
+        n_tiles = ceil_div(n_max > 0 ? n_max : 1, SCAN_TILE);
+        for (int k = 0; k < 2; k++) {
+            YB_CUDA(cudaMalloc(&status[k], n_tiles * sizeof(unsigned long long)));
+            YB_CUDA(cudaMemset(status[k], 0, n_tiles * sizeof(unsigned long long)));
         }
-        YB_CUDA(cudaMalloc(&status, n_tiles * sizeof(unsigned long long)));
-        YB_CUDA(cudaMemset(status, 0, n_tiles * sizeof(unsigned long long)));
         YB_CUDA(cudaMalloc(&scan_ctl, sizeof(Step_ctl)));
         Step_ctl fresh{};
         fresh.scan_epoch = 1;
         YB_CUDA(cudaMemcpy(
             scan_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        YB_CUDA(cudaMalloc(&n_stay, sizeof(int)));
         YB_CUDA(cudaMalloc(&new_count, sizeof(int)));
     }
     void release()
     {
-        for (int k = 0; k < 3; k++) {
-            cudaFree(flag[k]);
-            cudaFree(off[k]);
-        }
-        cudaFree(status);
+        cudaFree(status[0]);
+        cudaFree(status[1]);
         cudaFree(scan_ctl);
+        cudaFree(n_stay);
         cudaFree(new_count);
     }
 };

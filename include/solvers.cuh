@@ -402,30 +402,24 @@ public:
     // left the slab during the step.
     void slab_pack(int what, float* send_lo, float* send_hi)
     {
-        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         const bool migration = what == 2;
         const Pt* P = what == 1 ? d_X1 : d_X;
+        // halo: cells within `halo` of a cut; migration: cells beyond it
         const float lo_edge = migration ? slab.z_lo : slab.z_lo + slab.halo;
         const float hi_edge = migration ? slab.z_hi : slab.z_hi - slab.halo;
-        yb::slab_flags<Pt><<<blocks, 256, 0, stream>>>(d_ctl, P, lo_edge, hi_edge,
-            slab.has_lower, slab.has_upper, slab.flag[0], slab.flag[1],
-            migration ? slab.flag[2] : nullptr);
-        for (int k = 0; k < (migration ? 3 : 2); k++)
-            yb::scan_bins<<<slab.n_tiles, yb::SCAN_THREADS, 0, stream>>>(
-                slab.flag[k], slab.off[k], slab.n_tiles, slab.status,
-                slab.scan_ctl);
-        yb::slab_pack<Pt><<<blocks, 256, 0, stream>>>(d_ctl, P, d_old_v,
-            slab.off[0], slab.off[1], send_lo, send_hi, slab.capacity);
-        if (migration)  // X1 and dX are free at the end of a step: scratch
-            yb::slab_compact_stayers<Pt><<<blocks, 256, 0, stream>>>(d_ctl, d_X,
-                d_old_v, slab.off[2], d_X1, reinterpret_cast<float3*>(d_dX));
+        // X1 and dX are free at the end of a step: scratch for the stayers
+        yb::slab_select<Pt><<<slab.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
+            slab.scan_ctl, P, d_old_v, lo_edge, hi_edge, slab.has_lower,
+            slab.has_upper, migration, send_lo, send_hi, slab.capacity, d_X1,
+            reinterpret_cast<float3*>(d_dX), slab.n_stay, slab.status[0],
+            slab.status[1], slab.n_tiles);
         YB_CUDA(cudaGetLastError());
     }
     void slab_unpack(int what, const float* recv_lo, const float* recv_hi)
     {
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (what == 2) {
-            yb::slab_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, slab.off[2],
+            yb::slab_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, slab.n_stay,
                 d_X1, reinterpret_cast<const float3*>(d_dX), recv_lo, recv_hi,
                 slab.has_lower, slab.has_upper, n_max, d_X, d_old_v,
                 slab.new_count);
