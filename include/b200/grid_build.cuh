@@ -106,7 +106,7 @@ __device__ __forceinline__ int cube_of(float x, float y, float z,
     const long long iz = static_cast<long long>(floorf(z / cube_size)) + z_half;
     long long id = ix + iy * grid_size + iz * grid_size * grid_size;
     if (id < 0 || id >= n_cubes) {
-        atomicAdd(out_of_grid, 1);
+        if (out_of_grid) atomicAdd(out_of_grid, 1);  // nullptr: just recompute
         id = id < 0 ? 0 : n_cubes - 1;
     }
     return static_cast<int>(id);
@@ -373,6 +373,80 @@ __global__ void __launch_bounds__(256) reorder_cells(
             aux[size_t(dst) * L::aux_vec4 + q] = make_float4(
                 a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
 
+        cube_sorted[dst] = c;
+    }
+}
+
+// ---- steps 3 + 4 for large tissues: carry the state along ---------------------
+// place_ids + reorder_cells gather X, old_v and the key by original id: about
+// four random 32-byte sectors per cell, which is what bounds the build once
+// the state no longer fits the L2 (>= 10 M cells). The pair below reads the
+// state in original order instead -- sequentially -- and scatters one packed
+// record {x, y, z, bits(id), aux...} per cell to slot offset[cube] + arrival:
+// cube order, but arrival order inside a cube. settle_cells then puts every
+// cube into ascending id (ranks among 2-4 neighbouring records: sequential
+// reads, near-sequential writes) and writes the planes the sweep reads.
+template<typename Pt>
+__global__ void __launch_bounds__(256) place_cells(
+    const int* __restrict__ d_n, int n_max, const Pt* __restrict__ d_X,
+    const float3* __restrict__ d_old_v, const int* __restrict__ key,
+    const int* __restrict__ arrival, const int* __restrict__ offset,
+    float4* __restrict__ staged)
+{
+    using L = Layout<Pt>;
+    constexpr int REC = 1 + L::aux_vec4;  // float4s per staged record
+    const int n = live_cells(d_n, n_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += gridDim.x * blockDim.x) {
+        const int slot = __ldg(offset + __ldg(key + i)) + __ldg(arrival + i);
+        const Pt X = load_pt(d_X, i);
+        float4* record = staged + size_t(slot) * REC;
+        record[0] = make_float4(X.x, X.y, X.z, __int_as_float(i));
+
+        float a[L::aux_lanes];
+#pragma unroll
+        for (int e = 0; e < L::extras; e++) a[e] = lane(X, 3 + e);
+        const float* v = reinterpret_cast<const float*>(d_old_v + i);
+        a[L::v_lane + 0] = __ldg(v + 0);
+        a[L::v_lane + 1] = __ldg(v + 1);
+        a[L::v_lane + 2] = __ldg(v + 2);
+#pragma unroll
+        for (int e = L::v_lane + 3; e < L::aux_lanes; e++) a[e] = 0.f;
+#pragma unroll
+        for (int q = 0; q < L::aux_vec4; q++)
+            record[1 + q] = make_float4(
+                a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    }
+}
+
+template<typename Pt>
+__global__ void __launch_bounds__(256) settle_cells(
+    const int* __restrict__ d_n, int n_max, const float4* __restrict__ staged,
+    const int* __restrict__ offset, float cube_size, int grid_size, int z_half,
+    int n_cubes, float4* __restrict__ pos4, float4* __restrict__ aux,
+    int* __restrict__ cube_sorted)
+{
+    using L = Layout<Pt>;
+    constexpr int REC = 1 + L::aux_vec4;
+    const int n = live_cells(d_n, n_max);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += gridDim.x * blockDim.x) {
+        const float4 me = __ldg(staged + size_t(k) * REC);
+        // same arithmetic as the binning, so the same cube
+        const int c = cube_of(
+            me.x, me.y, me.z, cube_size, grid_size, z_half, n_cubes, nullptr);
+        const int start = __ldg(offset + c), end = __ldg(offset + c + 1);
+        const int id = __float_as_int(me.w);
+        int rank = 0;
+        for (int q = start; q < end; q++)
+            rank += __float_as_int(__ldg(
+                        reinterpret_cast<const float*>(staged + size_t(q) * REC) + 3)) < id;
+        const int dst = start + rank;
+        pos4[dst] = me;
+#pragma unroll
+        for (int q = 0; q < L::aux_vec4; q++)
+            aux[size_t(dst) * L::aux_vec4 + q] =
+                __ldg(staged + size_t(k) * REC + 1 + q);
         cube_sorted[dst] = c;
     }
 }

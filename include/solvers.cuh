@@ -873,11 +873,14 @@ public:
         YB_CUDA(cudaMalloc(
             &aux, cells * yb::Layout<Pt>::aux_vec4 * sizeof(float4)));
         YB_CUDA(cudaMalloc(&cube_sorted, cells * sizeof(int)));
+        YB_CUDA(cudaMalloc(&staged,
+            cells * (1 + yb::Layout<Pt>::aux_vec4) * sizeof(float4)));
     }
     Grid_computer(const Grid_computer&) = delete;
     Grid_computer& operator=(const Grid_computer&) = delete;
     ~Grid_computer()
     {
+        cudaFree(staged);
         cudaFree(cube_sorted);
         cudaFree(aux);
         cudaFree(pos4);
@@ -939,10 +942,35 @@ protected:
         const int tiles = yb::ceil_div(active_cubes + 1, yb::SCAN_TILE);
         yb::scan_bins<<<tiles, yb::SCAN_THREADS, 0, s>>>(
             sort.count, sort.offset, tiles, sort.status, d_ctl);
-        yb::place_ids<<<blocks, 256, 0, s>>>(
-            d_n, n_max, sort.key, sort.arrival, sort.offset, sort.slot_id);
-        yb::reorder_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, d_old_v,
-            sort.key, sort.offset, sort.slot_id, pos4, aux, cube_sorted);
+        if (carry_state()) {
+            yb::place_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, d_old_v,
+                sort.key, sort.arrival, sort.offset, staged);
+            yb::settle_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, staged,
+                sort.offset, cube_size, grid_size, z_half, active_cubes, pos4,
+                aux, cube_sorted);
+        } else {
+            yb::place_ids<<<blocks, 256, 0, s>>>(
+                d_n, n_max, sort.key, sort.arrival, sort.offset, sort.slot_id);
+            yb::reorder_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X,
+                d_old_v, sort.key, sort.offset, sort.slot_id, pos4, aux,
+                cube_sorted);
+        }
+    }
+
+    // Which of the two equivalent build tails to use (b200/grid_build.cuh):
+    // scattering the state along with the ids wins once the state outgrows
+    // the L2, provided a staged record is exactly one 32-byte sector (float3,
+    // float4: relu_10M 5.18 -> 4.73 ms/step; with the 48-byte records of
+    // Po_cell and the branching cell it loses 3 %). YALLA_B200_CARRY_STATE=0/1
+    // overrides.
+    bool carry_state() const
+    {
+        static const int forced = [] {
+            const char* env = getenv("YALLA_B200_CARRY_STATE");
+            return env && env[0] ? atoi(env) : -1;
+        }();
+        if (forced >= 0) return forced != 0;
+        return yb::Layout<Pt>::aux_vec4 == 1 && n_max >= 4 * 1000 * 1000;
     }
 
     // The first stage's index, built before the generic forces are known (they only
@@ -1002,6 +1030,7 @@ protected:
     float4* pos4;
     float4* aux;
     int* cube_sorted;
+    float4* staged;  // cube order, arrival order inside cubes (place_cells)
     const int n_max, grid_size, n_cubes;
     // z numbering of the grid: the reference's cubic grid by default; a slab of
     // a decomposed domain uses only its own layers (dd_slab_grid below)
