@@ -9,11 +9,13 @@ and, at the benchmark's full size, against size-independent properties
 Integer and index results must be bit-exact; floating point within 1e-5
 relative per step on the max-norm (north_star).
 """
+import os
+
 import numpy as np
 import pytest
 
 import make_golden
-from conftest import golden
+from conftest import ROOT, golden
 from helpers import assert_states_close, model_cases, run_case
 from yalla_b200 import workloads
 
@@ -475,3 +477,44 @@ def test_full_size_sample_vs_oracle(product, oracle):
                 types=None, links=None)
     got, want = run_case(product, case), run_case(oracle, case)
     assert_states_close(got["X_out"], want["X_out"], 2, "200k cells")
+
+
+# ---- the state-carrying grid build (place_cells + settle_cells) --------------------
+def test_state_carrying_build_matches_oracle(oracle, tmp_path):
+    """The build tail used for float3/float4 tissues with n_max >= 4 M is chosen
+    once per process; force it in a fresh interpreter and compare a small
+    tissue with the oracle (positions after 3 steps, Grid and Gabriel-free
+    models with and without extra lanes)."""
+    import subprocess
+    import sys
+    script = f"""
+import sys
+import numpy as np
+sys.path.insert(0, {ROOT!r})
+import yalla_b200 as yb
+from yalla_b200 import workloads
+rng = np.random.default_rng(21)
+product = yb.product()
+for model, lanes in (("relu_grid", 3), ("epithelium", 5)):
+    n = 30000
+    X = np.zeros((n, lanes), dtype=np.float32)
+    X[:, :5 if lanes == 5 else 3] = (workloads.polarized_ball(n, 0.8, rng)
+                                     if lanes == 5 else workloads.random_ball(n, 0.8, rng))
+    with product.sim(model, n, 60, 1.0) as sim:
+        sim.set_state(X)
+        sim.step(0.05, 3)
+        np.save(sys.argv[1] + "/" + model + ".npy", sim.get_state())
+    np.save(sys.argv[1] + "/" + model + "_in.npy", X)
+"""
+    env = dict(os.environ, YALLA_B200_CARRY_STATE="1")
+    result = subprocess.run([sys.executable, "-c", script, str(tmp_path)], env=env,
+                            capture_output=True, text=True, timeout=600)
+    assert result.returncode == 0, result.stderr[-2000:]
+    for model in ("relu_grid", "epithelium"):
+        X = np.load(tmp_path / f"{model}_in.npy")
+        got = np.load(tmp_path / f"{model}.npy")
+        with oracle.sim(model, len(X), 60, 1.0) as sim:
+            sim.set_state(X)
+            sim.step(0.05, 3)
+            want = sim.get_state()
+        assert_states_close(got, want, 3, f"carried build, {model}", 4.0)
