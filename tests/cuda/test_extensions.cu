@@ -1,18 +1,22 @@
 // GPU test program for header-level extensions that have no C-ABI entry:
-// Vtk_async_output against the synchronous Vtk_output, and the seeded
-// generators through the header API. Prints one "ok <name>" line per check
+// Vtk_async_output against the synchronous Vtk_output, the seeded generators
+// through the header API, and Cell_division. Prints one "ok <name>" line per check
 // and exits non-zero on the first failure (run by tests/test_extensions_gpu.py).
 #include <stdio.h>
 #include <stdlib.h>
 #include <fstream>
 #include <iterator>
 #include <string>
+#include <vector>
+#include <string.h>
 
 #include "../../include/dtypes.cuh"
 #include "../../include/inits.cuh"
 #include "../../include/polarity.cuh"
+#include "../../include/property.cuh"
 #include "../../include/solvers.cuh"
 #include "../../include/vtk.cuh"
+#include "../../include/b200/division.cuh"
 
 #define CHECK(cond, name)                                   \
     do {                                                    \
@@ -38,6 +42,87 @@ __device__ Po_cell layer(Po_cell Xi, Po_cell r, float dist, int i, int j)
     dF.x = r.x * F / dist, dF.y = r.y * F / dist, dF.z = r.z * F / dist;
     dF += bending_force(Xi, r, dist) * 0.2f;
     return dF;
+}
+
+// ---- Cell_division: a rate rule with a per-cell property to inherit -----------
+__device__ int* d_lineage;
+
+__device__ float divide_sometimes(int i, const Po_cell& X)
+{
+    return X.z > 0 ? 0.25f : 0.f;  // only the upper half of the tissue divides
+}
+
+__device__ void inherit_lineage(int mother, int daughter)
+{
+    d_lineage[daughter] = d_lineage[mother];
+}
+
+static void check_division()
+{
+    const int n = 50000, n_max = 80000;
+    std::vector<Po_cell> first_run;
+    std::vector<int> first_lineage;
+    int first_n = 0;
+    for (int run = 0; run < 2; run++) {
+        Solution<Po_cell, Grid_solver> cells{n_max, 64, 1.f};
+        Property<int> lineage{n_max, "lineage"};
+        cudaMemcpyToSymbol(d_lineage, &lineage.d_prop, sizeof(d_lineage));
+        *cells.h_n = n;
+        for (int i = 0; i < n_max; i++) {
+            cells.h_X[i] = Po_cell{0};
+            lineage.h_prop[i] = i < n ? i : -1;
+        }
+        cells.copy_to_device();
+        lineage.copy_to_device();
+        seeded_sphere(0.8f, cells, 9);
+        Cell_division<Po_cell> division{n_max, 1234};
+        int upper = 0;
+        for (int i = 0; i < n; i++) upper += cells.h_X[i].z > 0;
+
+        division.divide<divide_sometimes, inherit_lineage>(cells, 0.8f);
+        cells.copy_to_host();
+        lineage.copy_to_host();
+        const int n_1 = *cells.h_n;
+        if (run == 0) {
+            const double expected = 0.25 * upper, sigma = sqrt(0.25 * 0.75 * upper);
+            CHECK(fabs((n_1 - n) - expected) < 5 * sigma, "division count");
+            bool placed = true, inherited = true;
+            for (int j = n; j < n_1; j++) {
+                const int mother = lineage.h_prop[j];
+                inherited = inherited && mother >= 0 && mother < n &&
+                            cells.h_X[mother].z > 0;
+                if (!inherited) break;
+                const float dx = cells.h_X[j].x - cells.h_X[mother].x,
+                            dy = cells.h_X[j].y - cells.h_X[mother].y,
+                            dz = cells.h_X[j].z - cells.h_X[mother].z;
+                placed = placed && fabsf(sqrtf(dx * dx + dy * dy + dz * dz) - 0.2f) < 1e-4f;
+                // stable: daughters appear in the order of their mothers
+                if (j > n) inherited = inherited && lineage.h_prop[j - 1] < mother;
+            }
+            CHECK(inherited, "daughters inherit and are appended in mother order");
+            CHECK(placed, "daughters sit mean_dist / 4 from their mothers");
+        }
+        // second call: new draws (other mothers), and the tissue fills up
+        division.divide<divide_sometimes, inherit_lineage>(cells, 0.8f);
+        for (int k = 0; k < 6; k++)
+            division.divide<divide_sometimes, inherit_lineage>(cells, 0.8f);
+        cells.copy_to_host();
+        lineage.copy_to_host();
+        int before = 0, dropped = 0;
+        division.last_call(&before, &dropped);
+        if (run == 0) {
+            CHECK(*cells.h_n == n_max && dropped > 0, "full tissue drops divisions");
+            first_n = *cells.h_n;
+            first_run.assign(cells.h_X, cells.h_X + first_n);
+            first_lineage.assign(lineage.h_prop, lineage.h_prop + first_n);
+        } else {
+            bool same = *cells.h_n == first_n;
+            for (int i = 0; same && i < first_n; i++)
+                same = memcmp(&first_run[i], &cells.h_X[i], sizeof(Po_cell)) == 0 &&
+                       first_lineage[i] == lineage.h_prop[i];
+            CHECK(same, "division is reproducible bit for bit");
+        }
+    }
 }
 
 int main(int argc, char** argv)
@@ -111,6 +196,7 @@ int main(int argc, char** argv)
                   std::string::npos,
             "frame uses the device-side cell count");
     }
+    check_division();
     printf("all extension checks passed\n");
     return 0;
 }

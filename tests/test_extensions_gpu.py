@@ -1,7 +1,8 @@
 """Header-level extensions without a C-ABI entry, exercised by the CUDA test
 programs in tests/cuda/ (built into tests/_bin/ by yalla_b200/build.py):
-Vtk_async_output -- asynchronous frames identical to Vtk_output's -- and the
-seeded generators through the header API."""
+Vtk_async_output -- asynchronous frames identical to Vtk_output's --, the
+seeded generators through the header API, and Cell_division (reproducible
+cell division: count statistics, placement, inheritance, order, clamping)."""
 import os
 import subprocess
 
@@ -19,4 +20,4 @@ def test_extension_programs(tmp_path):
                             text=True, timeout=600)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
     assert "all extension checks passed" in result.stdout
-    assert result.stdout.count("ok ") >= 6
+    assert result.stdout.count("ok ") >= 11
