@@ -479,6 +479,37 @@ def test_full_size_sample_vs_oracle(product, oracle):
     assert_states_close(got["X_out"], want["X_out"], 2, "200k cells")
 
 
+def test_reproducible_division_growth(product):
+    """Growth with Cell_division (b200/division.cuh) instead of the example's
+    proliferate kernel: same division rule, but Philox keyed by (seed, cell,
+    step) and daughters appended in mother order -- two runs give the very same
+    arrays (with atomicAdd(d_n, 1) the daughters' slots differ from run to run),
+    and the growth rate matches the example's kernel statistically."""
+    n, steps = 40000, 12
+    rng = np.random.default_rng(5)
+    X = workloads.polarized_ball(n, 0.75, rng, lattice=True, noise=0.0)
+    types = workloads.shell_types(X)
+    X[types == 0, 3:5] = 0
+    gs = workloads.grid_size_for(n, 0.75, growth=2.0)
+    runs = {}
+    for mode in (1, 1, 0):
+        with product.sim("growth", 2 * n, gs, 1.0) as sim:
+            for key, value in (("prolif_rate", 0.02), ("mean_dist", 0.75), ("seed", 3),
+                               ("reproducible_division", mode)):
+                sim.set_param(key, value)
+            sim.set_ints("type", types)
+            sim.set_state(X)
+            sim.step(0.1, steps)
+            state = sim.get_state()
+            runs.setdefault(mode, []).append((state, sim.get_ints("type")))
+    (a, types_a), (b, types_b) = runs[1]
+    assert len(a) == len(b) > n
+    assert np.array_equal(a, b) and np.array_equal(types_a, types_b)
+    grown, grown_ref = len(a) - n, len(runs[0][0][0]) - n
+    assert abs(grown - grown_ref) < 0.1 * grown_ref + 50, (grown, grown_ref)
+    assert np.all(np.isfinite(a))
+
+
 # ---- the state-carrying grid build (place_cells + settle_cells) --------------------
 def test_state_carrying_build_matches_oracle(oracle, tmp_path):
     """The build tail used for float3/float4 tissues with n_max >= 4 M is chosen

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -571,6 +572,10 @@ struct Growth_sim : Typed_sim<Po_cell> {
     float prolif_rate = 0.006f, mean_dist = 0.75f;
     int seed = 2;
     bool seeded = false;
+#ifdef YALLA_B200
+    bool reproducible = false;
+    std::unique_ptr<Cell_division<Po_cell>> division;
+#endif
 
     Growth_sim(int n_max, int grid_size, float cube_size)
         : Typed_sim<Po_cell>{n_max, grid_size, cube_size}
@@ -592,6 +597,12 @@ struct Growth_sim : Typed_sim<Po_cell> {
         } else if (name == "seed") {
             seed = static_cast<int>(value);
             seeded = false;
+#ifdef YALLA_B200
+            division.reset();
+        } else if (name == "reproducible_division") {
+            // Cell_division instead of the example's proliferate kernel
+            reproducible = value != 0;
+#endif
         } else {
             const int fixed = Base::set_fix(name, value);
             return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
@@ -610,6 +621,17 @@ struct Growth_sim : Typed_sim<Po_cell> {
         auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
                              Po_cell* d_dX) { reset_counters(n); };
         cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
+#ifdef YALLA_B200
+        if (prolif_rate > 0 && reproducible) {
+            if (!division)
+                division.reset(new Cell_division<Po_cell>(n_max, seed));
+            cudaMemcpyToSymbolAsync(models::d_prolif_rate, &prolif_rate,
+                sizeof(float), 0, cudaMemcpyHostToDevice, model_stream());
+            division->divide<models::growth_division_rate, models::growth_inherit>(
+                cells, mean_dist);
+            return 0;
+        }
+#endif
         if (prolif_rate > 0) {
             // sized for the capacity; the kernel reads the live count itself
             models::snapshot_count<<<1, 1, 0, model_stream()>>>(

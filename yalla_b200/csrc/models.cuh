@@ -17,6 +17,9 @@
 #include "property.cuh"
 #include "solvers.cuh"
 #include "utils.cuh"
+#ifdef YALLA_B200  // extensions of this repo's headers
+#include "b200/division.cuh"
+#endif
 
 // Point types have to be declared at namespace scope (MAKE_PT specialises
 // Is_vector). 7-float cell of examples/branching.cu:57, and a 4-lane type for
@@ -159,6 +162,28 @@ __global__ void proliferate(float rate, float mean_dist, int n_max,
     d_epi_nbs[n] = 0;
     d_old_v[n] = d_old_v[i];
 }
+
+
+// The same division rule for Cell_division (b200/division.cuh, product build
+// only): mesenchyme divides with probability d_prolif_rate per step, an
+// epithelial cell whenever it has no more epithelial than mesenchymal
+// neighbours; the daughter inherits the type and starts with empty counters.
+#ifdef YALLA_B200
+__device__ float d_prolif_rate = 0.f;
+
+__device__ float growth_division_rate(int i, const Po_cell&)
+{
+    if (d_type[i] == mesenchyme) return d_prolif_rate;
+    return d_epi_nbs[i] > d_mes_nbs[i] ? 0.f : 1.f;
+}
+
+__device__ void growth_inherit(int mother, int daughter)
+{
+    d_type[daughter] = d_type[mother];
+    d_mes_nbs[daughter] = 0;
+    d_epi_nbs[daughter] = 0;
+}
+#endif
 
 
 // ---- 7-float Cell: branching ------------------------------------------------------
