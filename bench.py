@@ -603,7 +603,7 @@ def main():
     else:
         line["e2e"] = e2e
         line["roofline"] = roofline
-        line["gpu_launches"] = launches_per_step * steps
+        line["gpu_launches"] = launches_per_step * steps * world  # all ranks
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(spec)
     print(json.dumps(line))
