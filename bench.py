@@ -564,7 +564,8 @@ def main():
         # kernels of this repo per model step: stage 1 bin_cells, scan_bins,
         # place_ids, reorder_cells, sweep_cubes, predictor_step; stage 2 the
         # same minus bin_cells (fused into the predictor), corrector_step
-        launches_per_step = 11 + (1 if spec["model"] == "growth" else 0)
+        # (+ snapshot_count and proliferate in the growth model)
+        launches_per_step = 11 + (2 if spec["model"] == "growth" else 0)
     sim.close()
 
     if rank != 0:
