@@ -222,10 +222,11 @@ def sweep_traffic(workload):
     return None if entry is None else entry["dram_bytes_per_launch"]
 
 
-def cpu_baseline(spec, steps=2, sample_cells=200_000):
+def cpu_baseline(spec, steps=10, sample_cells=1_000_000):
     """The oracle (a CPU port of the reference's algorithm) on a bounded sample
-    of the workload: the same kind of tissue at sample_cells cells, division
-    switched off (no curand on the host)."""
+    of the workload: the same kind of tissue at up to sample_cells cells for a
+    few steps (about 10-20 s of host time with 16 cores), division switched off
+    (no curand on the host)."""
     lib = yb.load(ORACLE_LIB)
     small = dict(spec, n=min(spec["n"], sample_cells))
     small["n_max"] = small["n"]
