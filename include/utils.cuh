@@ -2,7 +2,7 @@
 #pragma once
 
 #include <curand_kernel.h>
-#include <sstream>
+#include <sstream>  // for user code that relies on it coming with utils.cuh
 #include <string>
 #include <vector>
 
@@ -13,9 +13,15 @@
 inline std::vector<std::string> split(const std::string& s)
 {
     std::vector<std::string> tokens;
-    std::istringstream stream(s);
-    for (std::string token; std::getline(stream, token, ' ');)
-        tokens.push_back(token);
+    for (size_t from = 0; from < s.size();) {
+        const size_t blank = s.find(' ', from);
+        if (blank == std::string::npos) {
+            tokens.push_back(s.substr(from));
+            break;
+        }
+        tokens.push_back(s.substr(from, blank - from));
+        from = blank + 1;
+    }
     return tokens;
 }
 

@@ -9,12 +9,15 @@
 #pragma once
 
 #include <assert.h>
+#include <stdint.h>
+#include <string.h>
 #include <sys/stat.h>
 #include <time.h>
 #include <fstream>
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <type_traits>
 #include <typeinfo>
 #include <vector>
 
@@ -206,6 +209,10 @@ void Vtk_output::write_property(Property<Prop>& property)
 }
 
 
+// Reads frames back by section keyword. Besides the ASCII frames of Vtk_output
+// it understands the BINARY frames of Vtk_async_output (big-endian payloads):
+// for those the sections are indexed once, by walking the file from payload to
+// payload, so that binary data is never mistaken for a keyword line.
 class Vtk_input {
 public:
     Vtk_input(std::string file_name);
@@ -226,118 +233,172 @@ public:
     int n_points;
 
 private:
+    struct Section {
+        std::string keyword, name;
+        std::streampos data;  // first byte behind the keyword line(s)
+    };
     std::string file_name;
+    bool binary = false;
+    std::vector<Section> sections;  // binary frames only
 
-    // Stream positioned on the first data line of the section.
-    std::ifstream open_at(std::string keyword1, std::string keyword2,
-        int lines_to_skip = 0)
+    void index_binary_sections();
+
+    // Hands the next `rows` records of `width` values of type T to
+    // take(i, values): one text line per record in ASCII frames (parsed like
+    // the reference does, with operator>> of T), 32-bit big-endian words
+    // otherwise.
+    template<typename T, typename Take>
+    void for_each_record(std::string keyword1, std::string keyword2,
+        int header_lines, int rows, int width, Take take)
     {
-        const std::streampos where = find_entry(keyword1, keyword2);
-        std::ifstream input_file(file_name);
-        assert(input_file.is_open());
-        input_file.seekg(where);
+        static_assert(sizeof(T) == 4, "legacy VTK float / int payloads");
+        std::ifstream file(file_name, std::ios::binary);
+        assert(file.is_open());
+        file.seekg(find_entry(keyword1, keyword2));
+        std::vector<T> values(width);
+        if (binary) {
+            std::vector<uint32_t> words(width);
+            for (int i = 0; i < rows; i++) {
+                file.read(reinterpret_cast<char*>(words.data()),
+                    width * sizeof(uint32_t));
+                for (int k = 0; k < width; k++) {
+                    const uint32_t bits = __builtin_bswap32(words[k]);
+                    memcpy(&values[k], &bits, sizeof(T));
+                }
+                take(i, values);
+            }
+            return;
+        }
         std::string line;
-        for (int i = 0; i < lines_to_skip; i++) getline(input_file, line);
-        return input_file;
+        for (int i = 0; i < header_lines; i++) getline(file, line);
+        for (int i = 0; i < rows; i++) {
+            getline(file, line);
+            std::istringstream text(line);
+            for (int k = 0; k < width; k++) text >> values[k];
+            take(i, values);
+        }
     }
 };
 
 inline Vtk_input::Vtk_input(std::string file_name) : file_name{file_name}
 {
-    std::ifstream input_file(file_name);
-    assert(input_file.is_open());
+    std::ifstream file(file_name, std::ios::binary);
+    assert(file.is_open());
 
-    // "POINTS <n> float" is on one of the first six lines
+    // line 3 names the encoding, "POINTS <n> float" is among the first six
     n_points = 0;
     std::string line;
     for (int i = 0; i < 6; i++) {
-        getline(input_file, line);
+        getline(file, line);
+        if (i == 2) binary = line.compare(0, 6, "BINARY") == 0;
         const auto items = split(line);
         if (items.size() > 1 && items[0] == "POINTS") {
             n_points = stoi(items[1]);
             break;
         }
     }
+    if (binary) index_binary_sections();
+}
+
+inline void Vtk_input::index_binary_sections()
+{
+    std::ifstream file(file_name, std::ios::binary);
+    std::string line;
+    for (int i = 0; i < 4; i++) getline(file, line);  // header
+    while (getline(file, line)) {
+        const auto items = split(line);
+        if (items.size() < 2) continue;  // blank separator lines
+        size_t payload = 0;
+        Section section{items[0], items[1], 0};
+        if (items[0] == "POINTS" || items[0] == "NORMALS") {
+            payload = size_t(n_points) * 3 * sizeof(float);
+        } else if (items[0] == "VERTICES") {
+            payload = size_t(stoi(items[1])) * 2 * sizeof(uint32_t);
+        } else if (items[0] == "SCALARS") {
+            getline(file, line);  // LOOKUP_TABLE default
+            payload = size_t(n_points) * sizeof(float);
+        } else if (items[0] == "POINT_DATA") {
+            continue;
+        } else {
+            break;  // unknown section: stop indexing rather than guess a size
+        }
+        section.data = file.tellg();
+        sections.push_back(section);
+        file.seekg(section.data + std::streamoff(payload));
+    }
 }
 
 inline std::streampos Vtk_input::find_entry(
     std::string keyword1, std::string keyword2)
 {
-    std::ifstream input_file(file_name);
-    assert(input_file.is_open());
-
-    std::string line;
-    for (int i = 0; i < 4; i++) getline(input_file, line);  // header
-
-    while (getline(input_file, line)) {
-        const auto items = split(line);
-        if (items.size() > 1 && items[0] == keyword1 && items[1] == keyword2)
-            return input_file.tellg();
+    if (binary) {
+        for (const auto& section : sections)
+            if (section.keyword == keyword1 && section.name == keyword2)
+                return section.data;
+    } else {
+        std::ifstream file(file_name);
+        assert(file.is_open());
+        std::string line;
+        for (int i = 0; i < 4; i++) getline(file, line);  // header
+        while (getline(file, line)) {
+            const auto items = split(line);
+            if (items.size() > 1 && items[0] == keyword1 && items[1] == keyword2)
+                return file.tellg();
+        }
     }
     std::cout << "Vtk_input: no entry \"" << keyword1 << " " << keyword2
               << "\" in " << file_name << std::endl;
     assert(false);
-    return input_file.tellg();
+    return std::streampos(0);
 }
 
 template<typename Pt, template<typename> class Solver>
 void Vtk_input::read_positions(Solution<Pt, Solver>& points)
 {
-    std::ifstream input_file = open_at("POINTS", std::to_string(n_points));
-    std::string line;
-    for (int i = 0; i < n_points; i++) {
-        getline(input_file, line);
-        const auto items = split(line);
-        points.h_X[i].x = stof(items[0]);
-        points.h_X[i].y = stof(items[1]);
-        points.h_X[i].z = stof(items[2]);
-    }
+    for_each_record<float>("POINTS", std::to_string(n_points), 0, n_points, 3,
+        [&](int i, const std::vector<float>& v) {
+            points.h_X[i].x = v[0];
+            points.h_X[i].y = v[1];
+            points.h_X[i].z = v[2];
+        });
 }
 
 template<typename Pt, template<typename> class Solver>
 void Vtk_input::read_polarity(Solution<Pt, Solver>& points)
 {
-    std::ifstream input_file = open_at("NORMALS", "polarity");
-    std::string line;
-    for (int i = 0; i < n_points; i++) {
-        getline(input_file, line);
-        const auto items = split(line);
-        const auto x = stof(items[0]);
-        const auto y = stof(items[1]);
-        const auto z = stof(items[2]);
-        const auto dist = sqrt(pow(x, 2) + pow(y, 2) + pow(z, 2));
-        if (dist == 0) {  // written for theta = phi = 0
-            points.h_X[i].phi = 0.0f;
-            points.h_X[i].theta = 0.0f;
-        } else {
-            points.h_X[i].phi = atan2(y, x);
-            points.h_X[i].theta = acos(z);  // the normals are unit vectors
-        }
-    }
+    for_each_record<float>("NORMALS", "polarity", 0, n_points, 3,
+        [&](int i, const std::vector<float>& v) {
+            const float x = v[0], y = v[1], z = v[2];
+            const auto length = sqrt(pow(x, 2) + pow(y, 2) + pow(z, 2));
+            if (length == 0) {  // written for theta = phi = 0
+                points.h_X[i].phi = 0.0f;
+                points.h_X[i].theta = 0.0f;
+            } else {  // the normals are unit vectors
+                points.h_X[i].phi = atan2(y, x);
+                points.h_X[i].theta = acos(z);
+            }
+        });
 }
 
 template<typename Pt, template<typename> class Solver>
 void Vtk_input::read_field(
     Solution<Pt, Solver>& points, const char* data_name, float Pt::*field)
 {
-    std::ifstream input_file = open_at("SCALARS", data_name, 1);  // LOOKUP_TABLE
-    std::string line;
-    for (int i = 0; i < n_points; i++) {
-        getline(input_file, line);
-        std::istringstream(line) >> points.h_X[i].*field;
-    }
+    for_each_record<float>("SCALARS", data_name, 1, n_points, 1,  // LOOKUP_TABLE
+        [&](int i, const std::vector<float>& v) { points.h_X[i].*field = v[0]; });
 }
 
 template<typename Prop>
 void Vtk_input::read_property(Property<Prop>& property, std::string prop_name)
 {
-    std::ifstream input_file = open_at("SCALARS", prop_name, 1);  // LOOKUP_TABLE
     assert(n_points <= property.n_max);
-    std::string line;
-    for (int i = 0; i < n_points; i++) {
-        getline(input_file, line);
-        std::istringstream(line) >> property.h_prop[i];
-    }
+    // float properties are stored as floats, everything else as int
+    using Stored = typename std::conditional<std::is_same<Prop, float>::value,
+        float, int>::type;
+    for_each_record<Stored>("SCALARS", prop_name, 1, n_points, 1,
+        [&](int i, const std::vector<Stored>& v) {
+            property.h_prop[i] = static_cast<Prop>(v[0]);
+        });
 }
 
 

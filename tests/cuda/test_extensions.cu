@@ -182,6 +182,28 @@ int main(int argc, char** argv)
         CHECK(first.find("BINARY") != std::string::npos &&
                   first.size() > size_t(n) * 12,
             "binary frame written");
+        // the binary frame reads back bit for bit; the ASCII one to 6 digits
+        Vtk_input binary_in{binary_out.frame_path(3)};
+        Vtk_input ascii_in{async_out.frame_path(3)};
+        Solution<Po_cell, Grid_solver> from_binary{n_max, 50, 1.f};
+        Solution<Po_cell, Grid_solver> from_ascii{n_max, 50, 1.f};
+        binary_in.read_positions(from_binary);
+        binary_in.read_field(from_binary, "theta", &Po_cell::theta);
+        ascii_in.read_positions(from_ascii);
+        ascii_in.read_polarity(from_ascii);
+        CHECK(binary_in.n_points == n && ascii_in.n_points == n, "frames hold n points");
+        bool close = true;
+        for (int i = 0; i < n; i++) {
+            // ASCII carries 6 significant digits; acos is ill-conditioned
+            // near the poles, so compare theta away from them
+            const float theta = from_binary.h_X[i].theta;
+            close = close &&
+                    fabsf(from_binary.h_X[i].x - from_ascii.h_X[i].x) <=
+                        1e-5f * fmaxf(1.f, fabsf(from_binary.h_X[i].x));
+            if (theta > 0.3f && theta < 2.8f)
+                close = close && fabsf(theta - from_ascii.h_X[i].theta) < 1e-4f;
+        }
+        CHECK(close, "binary and ASCII frames read back the same state");
     }
 
     // ---- a growing tissue: the frame holds the device-side count -----------
