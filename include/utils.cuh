@@ -39,7 +39,8 @@ __device__ __host__ float dot_product(Pt_a a, Pt_b b)
 // makes noisy runs comparable between the two builds for equal seeds.
 __global__ void setup_rand_states(int n_states, int seed, curandState* d_state)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_states) return;
-    curand_init(seed, i, 0, d_state + i);
+    // grid-stride, so any launch shape initialises all n_states generators
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_states; i += stride)
+        curand_init(seed, i, 0, d_state + i);
 }
