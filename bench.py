@@ -275,7 +275,7 @@ def run_decomposed(args, spec, rank, local_rank, world):
                            bounds[rank + 1], "cuda",
                            halo_capacity=face_cells * 13 // 10 + 4096)
     domain.set_cells(mine)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, 0.05)
     for _ in range(warmup):
         domain.step(dt)
 
@@ -425,7 +425,10 @@ def main():
     X, types, gs = make_state(spec, seed=1000 + rank)
     lanes = X.shape[1]
     steps = args.steps if not fallback_to_port else min(args.steps, 2)
-    sampler = ClockSampler(local_rank)  # NVML set-up happens before the warm-up
+    # NVML set-up happens before the warm-up. The product arm's steps make no
+    # driver calls that NVML could stall, so it is sampled every 10 ms; the
+    # reference arm (cudaMalloc/cudaFree every step) every 0.5 s.
+    sampler = ClockSampler(local_rank, 0.5 if is_reference else 0.01)
     sim = new_sim(lib, spec, X, types, gs)
     sim.step(spec["dt"], warmup if not fallback_to_port else 0)
     sim.sync()
