@@ -172,3 +172,64 @@ def test_ghosts_are_partners_only_gpu(product, oracle):
     assert sums["product"][0][3] == len(lower)
     assert np.allclose(sums["product"][0], sums["oracle"][0], rtol=1e-4, atol=1e-3)
     assert np.max(np.abs(sums["product"][1] - sums["oracle"][1])) < 1e-5 * 30
+
+
+def step_slabs_in_process(domains, dt):
+    """One decomposed Heun step of several slabs living in ONE process (same
+    device): SlabDomain.step with the neighbour exchange and the all-reduce
+    replaced by tensor copies -- every kernel of the multi-GPU path runs."""
+    def exchange():
+        for below, above in zip(domains[:-1], domains[1:]):
+            above.recv[0].copy_(below.send[1])
+            below.recv[1].copy_(above.send[0])
+
+    for what in (0, 1, 2):
+        for d in domains:
+            d.sim.slab_pack(what, d.send[0].data_ptr(), d.send[1].data_ptr())
+        exchange()
+        for d in domains:
+            d.sim.slab_unpack(what, d.recv[0].data_ptr(), d.recv[1].data_ptr())
+        if what == 2:
+            break
+        for d in domains:
+            d.sim.dd_forces(what, d.sums.data_ptr())
+        total = torch.stack([d.sums for d in domains]).sum(dim=0)
+        for d in domains:
+            d.sums.copy_(total)
+            d.sim.slab_update(what, dt, d.sums.data_ptr())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,lanes", [("relu_grid", 3), ("epithelium", 5)])
+def test_three_slabs_on_one_device_gpu(product, model, lanes):
+    # all decomposition kernels of the product (slab_select for halo and
+    # migration, ghost append, merge) for both record widths, against the
+    # single-domain product run
+    rng = np.random.default_rng(31)
+    n, steps, dt = 60000, 6, 0.05
+    if lanes == 3:
+        X = workloads.lattice_ball(n, 0.8, rng)
+    else:
+        X = workloads.polarized_ball(n, 0.8, rng, lattice=True)
+    gs = workloads.grid_size_for(n, 0.8)
+    want = single_domain(product, model, X, dt, steps, gs)
+    bounds = [-np.inf, -4.0, 3.0, np.inf]
+    domains = []
+    for z_lo, z_hi in zip(bounds[:-1], bounds[1:]):
+        d = dd.SlabDomain(product, model, n, gs, 1.0, z_lo, z_hi, "cuda")
+        d.set_cells(X[(X[:, 2] >= z_lo) & (X[:, 2] < z_hi)])
+        domains.append(d)
+    start = [d.n_owned for d in domains]
+    for _ in range(steps):
+        step_slabs_in_process(domains, dt)
+    parts = [d.owned_state()[0].cpu().numpy() for d in domains]
+    problems = [d.counts()[2] for d in domains]
+    for d in domains:
+        d.close()
+    assert problems == [0, 0, 0]
+    got = np.concatenate(parts)
+    assert len(got) == n and sum(start) == n
+    for part, (z_lo, z_hi) in zip(parts, zip(bounds[:-1], bounds[1:])):
+        assert np.all(part[:, 2] >= z_lo) and np.all(part[:, 2] < z_hi)  # migrated
+    deviation = match_cells(got, want, 1e-4)
+    assert deviation < 1e-5 * steps * max(np.abs(want).max(), 1.0) * 4
