@@ -218,6 +218,43 @@ int main(int argc, char** argv)
                   std::string::npos,
             "frame uses the device-side cell count");
     }
+    // ---- seeded box, plain and relaxed --------------------------------------
+    {
+        Solution<float3, Grid_solver> box{20000, 50, 1.f};
+        const float3 lo{-3.f, -2.f, -1.f}, hi{5.f, 4.f, 3.f};
+        seeded_cuboid(0.8f, lo, hi, box, 77);
+        const double expected = 8. * 6. * 4. / (4. / 3 * M_PI * 0.4 * 0.4 * 0.4) * 0.64;
+        CHECK(*box.h_n == int(expected) && box.get_d_n() == *box.h_n,
+            "seeded_cuboid places the packing-fraction count");
+        bool inside = true;
+        double mean_x = 0;
+        for (int i = 0; i < *box.h_n; i++) {
+            const float3 X = box.h_X[i];
+            inside = inside && X.x > lo.x && X.x <= hi.x && X.y > lo.y && X.y <= hi.y &&
+                     X.z > lo.z && X.z <= hi.z;
+            mean_x += X.x / *box.h_n;
+        }
+        CHECK(inside && fabs(mean_x - 1.0) < 0.2, "seeded_cuboid fills the box uniformly");
+
+        Solution<float3, Grid_solver> relaxed{20000, 50, 1.f};
+        relaxed_seeded_cuboid(0.75f, lo, hi, relaxed, 78, 0, 300);
+        float nearest_min = 1e9f;
+        const int m = *relaxed.h_n;
+        for (int i = 0; i < 200; i++) {  // a sample of cells
+            float nearest = 1e9f;
+            for (int j = 0; j < m; j++) {
+                if (j == i) continue;
+                const float dx = relaxed.h_X[i].x - relaxed.h_X[j].x,
+                            dy = relaxed.h_X[i].y - relaxed.h_X[j].y,
+                            dz = relaxed.h_X[i].z - relaxed.h_X[j].z;
+                nearest = fminf(nearest, sqrtf(dx * dx + dy * dy + dz * dz));
+            }
+            nearest_min = fminf(nearest_min, nearest);
+        }
+        CHECK(m > 400 && nearest_min > 0.4f * 0.75f,
+            "relaxed_seeded_cuboid pushes overlapping cells apart");
+    }
+
     check_division();
     printf("all extension checks passed\n");
     return 0;

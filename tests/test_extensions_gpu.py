@@ -20,4 +20,4 @@ def test_extension_programs(tmp_path):
                             text=True, timeout=600)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
     assert "all extension checks passed" in result.stdout
-    assert result.stdout.count("ok ") >= 13
+    assert result.stdout.count("ok ") >= 16
