@@ -16,6 +16,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "grid_build.cuh"
 #include "layout.cuh"
@@ -60,8 +61,16 @@ __device__ __forceinline__ void read_record(
 // writes its records straight to their final positions. In a migration round
 // every cell goes exactly one way, so the rank of a cell that stays is its
 // index minus the cells before it that leave: the stayers are compacted in the
-// same pass. The order of records is ascending cell index, exactly as with the
-// separate passes.
+// same pass. The order of records is ascending cell index.
+//
+// Cell identity is not tracked across a decomposed run, so a migration round
+// may also PERMUTE the cells that stay: with `order` (the cube-ordered pos4 of
+// the last force evaluation, original index in .w) the pass walks the cells in
+// cube order and compacts them in that order. From the second step on the
+// slab's own storage order is then nearly cube order, which turns the
+// scattered record writes of the next grid builds (place_cells) and the
+// scattered force stores of the sweeps into near-sequential traffic. A third
+// running count (entries of `order` that are ghosts) gives the ranks.
 constexpr int SELECT_SUB = SCAN_TILE / SCAN_THREADS;  // cells per thread
 
 template<typename Pt>
@@ -70,14 +79,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
     float lo_edge, float hi_edge, int has_lower, int has_upper, int migration,
     float* __restrict__ send_lo, float* __restrict__ send_hi, int capacity,
     Pt* __restrict__ X_tmp, float3* __restrict__ v_tmp, int* n_stay,
-    unsigned long long* status_lo, unsigned long long* status_hi, int n_tiles)
+    unsigned long long* status_lo, unsigned long long* status_hi, int n_tiles,
+    const float4* __restrict__ order, const int* __restrict__ d_n_total,
+    int n_max, unsigned long long* status_ghost)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
     constexpr int WARPS = SCAN_THREADS / 32;
     __shared__ int s_tile;
-    __shared__ int s_count[2][SELECT_SUB][WARPS];  // then: exclusive prefixes
-    __shared__ int s_total[2];
-    __shared__ int s_tile_prefix[2];
+    __shared__ int s_count[3][SELECT_SUB][WARPS];  // then: exclusive prefixes
+    __shared__ int s_total[3];
+    __shared__ int s_tile_prefix[3];
 
     const int t = threadIdx.x;
     const int lane_id = t & 31, warp_id = t >> 5;
@@ -86,32 +97,48 @@ __global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
     const int tile = s_tile;
     const unsigned epoch =
         static_cast<unsigned>(*(volatile int*)&scan_ctl->scan_epoch) & 0x3fffffffu;
-    const int n = ctl->n_owned;
+    const int n_owned = ctl->n_owned;
+    const bool permute = order != nullptr;
+    // entries to walk: the owned cells, or every slot of `order` (with ghosts)
+    const int n = permute ? live_cells(d_n_total, n_max) : n_owned;
     const int first = tile * SCAN_TILE;
 
-    // sub-block u holds cells first + u * THREADS + t: coalesced, and ranks in
-    // (u, warp, lane) order are ranks in cell order
+    // sub-block u holds entries first + u * THREADS + t: coalesced, and ranks
+    // in (u, warp, lane) order are ranks in entry order
     unsigned flags = 0;  // bit 2u: goes down, bit 2u + 1: goes up
+    unsigned ghosts = 0;  // bit u: the entry is a ghost (permuted walk only)
+    int cell[SELECT_SUB];
 #pragma unroll
     for (int u = 0; u < SELECT_SUB; u++) {
-        const int i = first + u * SCAN_THREADS + t;
-        int lo = 0, hi = 0;
-        if (i < n) {
-            const float z = __ldg(reinterpret_cast<const float*>(P + i) + 2);
-            lo = has_lower && z < lo_edge;
-            hi = has_upper && z >= hi_edge;
+        const int q = first + u * SCAN_THREADS + t;
+        int lo = 0, hi = 0, ghost = 0;
+        cell[u] = q;
+        if (q < n) {
+            if (permute) {
+                cell[u] = __float_as_int(__ldg(&order[q].w));
+                ghost = cell[u] >= n_owned;
+            }
+            if (!ghost) {
+                const float z =
+                    __ldg(reinterpret_cast<const float*>(P + cell[u]) + 2);
+                lo = has_lower && z < lo_edge;
+                hi = has_upper && z >= hi_edge;
+            }
         }
         flags |= (unsigned(lo) << (2 * u)) | (unsigned(hi) << (2 * u + 1));
+        ghosts |= unsigned(ghost) << u;
         const unsigned lo_mask = __ballot_sync(0xffffffffu, lo);
         const unsigned hi_mask = __ballot_sync(0xffffffffu, hi);
+        const unsigned ghost_mask = __ballot_sync(0xffffffffu, ghost);
         if (lane_id == 0) {
             s_count[0][u][warp_id] = __popc(lo_mask);
             s_count[1][u][warp_id] = __popc(hi_mask);
+            s_count[2][u][warp_id] = __popc(ghost_mask);
         }
     }
     __syncthreads();
-    // exclusive scan of the SUB x WARPS counts, one warp per direction
-    if (warp_id < 2) {
+    // exclusive scan of the SUB x WARPS counts, one warp per running count
+    if (warp_id < (permute ? 3 : 2)) {
         constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
         int* counts = &s_count[warp_id][0][0];
         int mine[PER_LANE], sum = 0;
@@ -133,8 +160,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
             running += mine[q];
         }
         const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
-        const int exclusive = scan_lookback(warp_id == 0 ? status_lo : status_hi,
-            tile, epoch, aggregate, lane_id);
+        unsigned long long* const status =
+            warp_id == 0 ? status_lo : (warp_id == 1 ? status_hi : status_ghost);
+        const int exclusive =
+            scan_lookback(status, tile, epoch, aggregate, lane_id);
         if (lane_id == 0) {
             s_total[warp_id] = aggregate;
             s_tile_prefix[warp_id] = exclusive;
@@ -142,29 +171,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
     }
     __syncthreads();
     const int prefix_lo = s_tile_prefix[0], prefix_hi = s_tile_prefix[1];
+    const int prefix_ghost = permute ? s_tile_prefix[2] : 0;
 
 #pragma unroll
     for (int u = 0; u < SELECT_SUB; u++) {
-        const int i = first + u * SCAN_THREADS + t;
+        const int q = first + u * SCAN_THREADS + t;
+        const int i = cell[u];
         const int lo = (flags >> (2 * u)) & 1, hi = (flags >> (2 * u + 1)) & 1;
+        const int ghost = (ghosts >> u) & 1;
         const unsigned lo_mask = __ballot_sync(0xffffffffu, lo);
         const unsigned hi_mask = __ballot_sync(0xffffffffu, hi);
+        const unsigned ghost_mask = __ballot_sync(0xffffffffu, ghost);
         const unsigned below = (1u << lane_id) - 1u;
         const int a = prefix_lo + s_count[0][u][warp_id] + __popc(lo_mask & below);
         const int b = prefix_hi + s_count[1][u][warp_id] + __popc(hi_mask & below);
-        if (i >= n) continue;
+        const int g = permute ? prefix_ghost + s_count[2][u][warp_id] +
+                                    __popc(ghost_mask & below)
+                              : 0;
+        if (q >= n || ghost) continue;
         if (lo && a < capacity)
             write_record(send_lo + SLAB_HEADER + size_t(a) * W, P, v, i);
         if (hi && b < capacity)
             write_record(send_hi + SLAB_HEADER + size_t(b) * W, P, v, i);
         if (migration && !lo && !hi) {
-            const int to = i - a - b;
+            const int to = q - a - b - g;
             store_pt(X_tmp, to, load_pt(P, i));
             v_tmp[to] = v[i];
         }
     }
 
-    // the tile that holds the last owned cell knows the totals
+    // the tile that holds the last entry knows the totals
     const int last_tile = n > 0 ? (n - 1) / SCAN_TILE : 0;
     if (t == 0 && tile == last_tile) {
         const int n_lo = prefix_lo + s_total[0], n_hi = prefix_hi + s_total[1];
@@ -172,7 +208,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) slab_select(Step_ctl* ctl,
             atomicAdd(&ctl->out_of_grid, 1 << 20);
         send_lo[0] = __int_as_float(min(n_lo, capacity));
         send_hi[0] = __int_as_float(min(n_hi, capacity));
-        if (migration) *n_stay = n - n_lo - n_hi;
+        if (migration) *n_stay = n_owned - n_lo - n_hi;
     }
     // The last tile to finish re-arms the control words for the next launch.
     if (t == 0) {
@@ -261,17 +297,23 @@ __global__ void slab_set_drift(Step_ctl* ctl, int stage, const float* sums4)
 struct Slab_scratch {
     int capacity = 0;     // records per exchange buffer
     int n_tiles = 0;      // tiles of SCAN_TILE cells covering n_max
-    unsigned long long* status[2] = {nullptr, nullptr};
+    unsigned long long* status[3] = {nullptr, nullptr, nullptr};
     Step_ctl* scan_ctl = nullptr;  // scan bookkeeping only
     int* n_stay = nullptr;
     int* new_count = nullptr;
     float z_lo = 0.f, z_hi = 0.f, halo = 0.f;
     int has_lower = 0, has_upper = 0;
+    // migration rounds re-store the owned cells in cube order
+    // (YALLA_B200_SLAB_PERMUTE=0 keeps their index order)
+    bool permute = [] {
+        const char* env = getenv("YALLA_B200_SLAB_PERMUTE");
+        return !(env && env[0] == '0');
+    }();
 
     void allocate(int n_max)
     {
         n_tiles = ceil_div(n_max > 0 ? n_max : 1, SCAN_TILE);
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < 3; k++) {
             YB_CUDA(cudaMalloc(&status[k], n_tiles * sizeof(unsigned long long)));
             YB_CUDA(cudaMemset(status[k], 0, n_tiles * sizeof(unsigned long long)));
         }
@@ -287,6 +329,7 @@ struct Slab_scratch {
     {
         cudaFree(status[0]);
         cudaFree(status[1]);
+        cudaFree(status[2]);
         cudaFree(scan_ctl);
         cudaFree(n_stay);
         cudaFree(new_count);

@@ -412,7 +412,11 @@ public:
             slab.scan_ctl, P, d_old_v, lo_edge, hi_edge, slab.has_lower,
             slab.has_upper, migration, send_lo, send_hi, slab.capacity, d_X1,
             reinterpret_cast<float3*>(d_dX), slab.n_stay, slab.status[0],
-            slab.status[1], slab.n_tiles);
+            slab.status[1], slab.n_tiles,
+            // migration: leave the cells that stay in the cube order of the
+            // last force evaluation (cell identity is not tracked anyway)
+            migration && slab.permute ? Computer<Pt>::dd_cube_order() : nullptr,
+            d_n, n_max, slab.status[2]);
         YB_CUDA(cudaGetLastError());
     }
     void slab_unpack(int what, const float* recv_lo, const float* recv_hi)
@@ -647,6 +651,8 @@ public:
 
 protected:
     float graph_key() const { return split_pairs ? 1.f : 0.f; }
+
+    const float4* dd_cube_order() const { return nullptr; }
 
     // nothing to prepare ahead of the generic forces
     void index_ahead(
@@ -972,6 +978,9 @@ protected:
         if (forced >= 0) return forced != 0;
         return yb::Layout<Pt>::aux_vec4 == 1 && n_max >= 4 * 1000 * 1000;
     }
+
+    // pos4 of the last build: cube order with the original index in .w
+    const float4* dd_cube_order() const { return pos4; }
 
     // The first stage's index, built before the generic forces are known (they only
     // seed dX); the next pwints() call then goes straight to the sweep.

@@ -139,7 +139,8 @@ def test_single_slab_matches_plain_step_gpu(product):
         domain.step(0.1)
     got = domain.owned_state()[0].cpu().numpy()
     domain.close()
-    assert np.max(np.abs(got - want)) < 1e-5 * 5 * np.abs(want).max()
+    # (migration rounds re-store the cells in cube order: compare as sets)
+    assert match_cells(got, want, 1e-4) < 1e-5 * 5 * np.abs(want).max()
 
 
 @pytest.mark.gpu
