@@ -243,17 +243,31 @@ def cpu_baseline(spec, steps=10, sample_cells=1_000_000):
             "cores": cores, "kind": "port", "sample": sample}
 
 
-def run_decomposed(args, spec, rank, local_rank, world):
-    """One tissue over `world` GPUs: slabs, halo exchange, global drift."""
+def pin_to_gpu_cpus(local_rank):
+    """Bind this rank to the CPU cores next to its GPU (NVML's affinity mask),
+    before any pinned host buffer is allocated: first touch then places the
+    buffers on the GPU's NUMA node, and the ranks of a multi-GPU run stop
+    sharing one socket's memory controllers for their host copies."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
+                   cells_total=None, e2e=True):
+    """One tissue over `world` GPUs: slabs, halo exchange, global drift. The
+    process group (NCCL) must be up when world > 1. Returns the bench record on
+    rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
     from yalla_b200 import dd
-
-    warmup = max(args.warmup, 3)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         if world > 1:
@@ -261,7 +275,7 @@ def run_decomposed(args, spec, rank, local_rank, world):
         torch.cuda.synchronize()
 
     d, dt = spec["d"], spec["dt"]
-    n_target = spec["cells_per_gpu"] * world
+    n_target = cells_total or spec["cells_per_gpu"] * world
     radius = (n_target * d ** 3 / np.sqrt(2.0) * 3.0 / (4.0 * np.pi)) ** (1.0 / 3.0)
     gs = int(np.ceil(2 * (radius + d))) + 4
     gs += gs % 2
@@ -283,7 +297,7 @@ def run_decomposed(args, spec, rank, local_rank, world):
     barrier()
     sampler.start()
     start.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         domain.step(dt)
     stop.record()
     barrier()
@@ -292,17 +306,20 @@ def run_decomposed(args, spec, rank, local_rank, world):
     n_mine = domain.n_owned
 
     # end to end: host buffers in and out every step
-    host_X = torch.from_numpy(mine).pin_memory()
-    e2e_steps = max(2, args.steps // 4)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        domain.set_cells(host_X)
-        domain.step(dt)
-        X_out, _ = domain.owned_state()
-        host_out = X_out.cpu()
-    barrier()
-    e2e_seconds = time.perf_counter() - t0
+    e2e_seconds, e2e_steps, n_out = 0.0, 0, 0
+    if e2e:
+        host_X = torch.from_numpy(mine).pin_memory()
+        e2e_steps = max(2, steps // 4)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            domain.set_cells(host_X)
+            domain.step(dt)
+            X_out, _ = domain.owned_state()
+            host_out = X_out.cpu()
+        barrier()
+        e2e_seconds = time.perf_counter() - t0
+        n_out = len(host_out)
 
     # the dominant kernel, timed alone
     domain.sim.profile_sweeps(True)
@@ -312,7 +329,8 @@ def run_decomposed(args, spec, rank, local_rank, world):
     domain.sim.profile_sweeps(False)
     owned, with_ghosts, problems = domain.counts()
 
-    stats = torch.tensor([ms, e2e_seconds, float(n_mine), float(len(host_out))],
+    stats = torch.tensor([ms, e2e_seconds, float(n_mine), float(n_out),
+                          float(with_ghosts - owned)],
                          dtype=torch.float64, device="cuda")
     if world > 1:
         worst = stats.clone()
@@ -320,47 +338,69 @@ def run_decomposed(args, spec, rank, local_rank, world):
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         ms, e2e_seconds = float(worst[0]), float(worst[1])
     cells_total = int(stats[2])
+    ghosts_total = int(stats[4])
     domain.close()
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(
-            peaks_path) else 6650.0
-        avg_ms = sweep_ms / max(sweep_launches, 1)
-        achieved = with_ghosts * (2 * 12 + 12) / (avg_ms * 1e-3) / 1e9
-        value = cells_total * args.steps / (ms * 1e-3)
-        line = {
-            "metric": "Heun-step cell-updates/s (Grid_solver)", "value": value,
-            "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": spec["model"],
-                       "cells_total": cells_total,
-                       "cells_per_gpu": spec["cells_per_gpu"], "grid_size": gs,
-                       "dt": dt, "parallelism": f"z-slabs x{world}, halo exchange "
-                       "+ migration over NCCL send/recv, drift all-reduce",
-                       "tissue": "jittered FCC ball, shuffled order, seeded",
-                       "l2": "working set (>1 GB per rank) exceeds the 126 MB L2"},
-            "clocks": clocks,
-            "e2e": {"value": cells_total * e2e_steps / e2e_seconds,
-                    "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": cells_total * 12,
-                    "d2h_bytes_per_step": cells_total * 12, "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "kernel": "sweep_cubes",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "avg_launch_ms": avg_ms,
-                         "share_of_step": 2 * avg_ms / (ms / args.steps),
-                         "note": "rank 0; instruction-issue bound, see DESIGN.md"},
-            # per step: 3 pack rounds (flags, 2-3 scans, pack, [compact]), 3
-            # unpacks (+ commit), 2 x (bin, scan, place, reorder, sweep), 2 x
-            # (set_drift, update) on every rank
-            "gpu_launches": 35 * args.steps * world,
-            "problems": problems,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(
+        peaks_path) else 6650.0
+    avg_ms = sweep_ms / max(sweep_launches, 1)
+    achieved = with_ghosts * (2 * 12 + 12) / (avg_ms * 1e-3) / 1e9
+    value = cells_total * steps / (ms * 1e-3)
+    line = {
+        "metric": "Heun-step cell-updates/s (Grid_solver)", "value": value,
+        "unit": "cell-updates/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "model": spec["model"],
+                   "cells_total": cells_total,
+                   "cells_per_gpu": cells_total // world, "grid_size": gs,
+                   "dt": dt, "parallelism": f"z-slabs x{world}, halo exchange "
+                   "+ migration over NCCL send/recv, drift all-reduce",
+                   "tissue": "jittered FCC ball, shuffled order, seeded",
+                   "l2": "working set (>1 GB per rank) exceeds the 126 MB L2"},
+        "clocks": clocks,
+        "ghost_cells": ghosts_total,
+        "roofline": {"bound": "hbm", "kernel": "sweep_cubes",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "avg_launch_ms": avg_ms,
+                     "share_of_step": 2 * avg_ms / (ms / steps),
+                     "note": "rank 0; instruction-issue bound, see DESIGN.md"},
+        # per step: 3 pack rounds (flags, 2-3 scans, pack, [compact]), 3
+        # unpacks (+ commit), 2 x (bin, scan, place, reorder, sweep), 2 x
+        # (set_drift, update) on every rank
+        "gpu_launches": 35 * steps * world,
+        "problems": problems,
+    }
+    if e2e:
+        line["e2e"] = {"value": cells_total * e2e_steps / e2e_seconds,
+                       "unit": "cell-updates/s",
+                       "h2d_bytes_per_step": cells_total * 12,
+                       "d2h_bytes_per_step": cells_total * 12, "steps": e2e_steps}
+    return line
+
+
+def time_reference(lib, spec, X, types, gs, steps, warmup, repeats):
+    """Best of `repeats` runs of the reference build; every run starts from the
+    same state as the product arm (state and types reloaded, `warmup` untimed
+    steps, then `steps` timed ones). The reference allocates and frees Thrust
+    temporaries every step and single timings scatter by up to 10x on this
+    pool, so the best run is the conservative bar."""
+    best = None
+    with new_sim(lib, spec, X, types, gs) as sim:
+        for _ in range(repeats):
+            if types is not None:
+                sim.set_ints("type", types)
+            sim.set_state(X)
+            sim.step(spec["dt"], warmup)
+            sim.sync()
+            ms, updates = sim.step_timed(spec["dt"], steps)
+            if best is None or updates / ms > best[1] / best[0]:
+                best = (ms, updates, sim.n())
+    return best
 
 
 def main():
@@ -373,6 +413,8 @@ def main():
     parser.add_argument("--workload", default="growth_1M",
                         choices=sorted(WORKLOADS) + sorted(DD_WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-decomposed", action="store_true",
+                        help="skip the slab-decomposed sphere record")
     args = parser.parse_args()
     warmup = max(args.warmup, 3)
 
@@ -382,72 +424,118 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     is_reference = args.impl == "reference"
 
-    if args.workload in DD_WORKLOADS:
-        dd_spec = DD_WORKLOADS[args.workload]
-        if not is_reference:
-            return run_decomposed(args, dd_spec, rank, local_rank, world)
-        # the reference is single-GPU: it integrates one rank's share
-        args.workload_note = "one rank's share of " + args.workload
-        spec = dict(model=dd_spec["model"], n=dd_spec["cells_per_gpu"],
-                    n_max=dd_spec["cells_per_gpu"], d=dd_spec["d"],
-                    dt=dd_spec["dt"], params={}, typed=False)
-    else:
-        spec = WORKLOADS[args.workload]
-
     if is_reference and rank != 0:
         return  # the reference arm runs on rank 0 alone
+    cpus = pin_to_gpu_cpus(local_rank if not is_reference else 0)
 
     use_dist = world > 1 and not is_reference
+    torch.cuda.set_device(local_rank if not is_reference else 0)
     if use_dist:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank if not is_reference else 0)
 
     def barrier():
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    fallback_to_port = False
-    if is_reference:
-        if os.path.exists(yb.REFERENCE_LIB):
-            lib = yb.reference()
-        else:
-            lib = yb.load(ORACLE_LIB)  # no reference build here: the CPU port
-            fallback_to_port = True
-            spec = dict(spec, params=dict(spec["params"], prolif_rate=0.0))
+    if args.workload in DD_WORKLOADS:
+        dd_spec = DD_WORKLOADS[args.workload]
+        if not is_reference:
+            line = run_decomposed(args.steps, warmup, dd_spec, args.workload,
+                                  rank, local_rank, world)
+            if rank == 0:
+                print(json.dumps(line))
+            if use_dist:
+                dist.destroy_process_group()
+            return
+        # the reference is single-GPU: it integrates one rank's share
+        spec = dict(model=dd_spec["model"], n=dd_spec["cells_per_gpu"],
+                    n_max=dd_spec["cells_per_gpu"], d=dd_spec["d"],
+                    dt=dd_spec["dt"], params={}, typed=False)
     else:
-        lib = yb.product()
+        spec = WORKLOADS[args.workload]
 
     X, types, gs = make_state(spec, seed=1000 + rank)
     lanes = X.shape[1]
-    steps = args.steps if not fallback_to_port else min(args.steps, 2)
-    # NVML set-up happens before the warm-up. The product arm's steps make no
-    # driver calls that NVML could stall, so it is sampled every 10 ms; the
-    # reference arm (cudaMalloc/cudaFree every step) every 0.5 s.
-    sampler = ClockSampler(local_rank, 0.5 if is_reference else 0.01)
+    steps = args.steps
+    config = {"workload": args.workload, "model": spec["model"],
+              "cells_start": spec["n"], "n_max": spec["n_max"], "grid_size": gs,
+              "dt": spec["dt"],
+              "tissue": "jittered FCC ball, shuffled order, seeded",
+              "l2": "working set (>300 MB per tissue) exceeds the 126 MB L2",
+              "parallelism": "1 GPU" if (is_reference or world == 1) else
+              f"independent tissues x{world} (+ one decomposed tissue, see "
+              "`decomposed`)"}
+
+    # ======================= the reference arm ============================
+    if is_reference:
+        sampler = ClockSampler(0, 0.5)  # sparse: NVML stalls cudaMalloc/cudaFree
+        if os.path.exists(yb.REFERENCE_LIB):
+            builds = {"-O3 (README flags, asserts on)": yb.REFERENCE_LIB}
+            if os.path.exists(yb.REFERENCE_NDEBUG_LIB):
+                builds["-O3 -DNDEBUG"] = yb.REFERENCE_NDEBUG_LIB
+            sampler.start()
+            timings = {}
+            for flags, path in builds.items():
+                timings[flags] = time_reference(yb.load(path), spec, X, types, gs,
+                                                steps, warmup, repeats=3)
+            clocks = sampler.stop()
+            flags = max(timings, key=lambda f: timings[f][1] / timings[f][0])
+            ms, updates, n_end = timings[flags]
+            kind, cores = "reference", 0
+            sample = ("the reference's own CUDA build (unmodified headers, "
+                      f"sm_100a, {flags}: the faster of {len(builds)} builds) "
+                      "on the full workload; ya||a has no CPU path")
+            builds_report = {f: t[1] / (t[0] * 1e-3) for f, t in timings.items()}
+        else:
+            # no reference build travelled with the snapshot: the CPU port
+            port = dict(spec, params=dict(spec["params"], prolif_rate=0.0)) \
+                if "prolif_rate" in spec["params"] else spec
+            steps = min(steps, 2)
+            sampler.start()
+            with new_sim(yb.load(ORACLE_LIB), port, X, types, gs) as sim:
+                ms, updates = sim.step_timed(spec["dt"], steps)
+                n_end = sim.n()
+            clocks = sampler.stop()
+            kind, cores = "port", os.cpu_count()
+            sample, builds_report = "CPU oracle port, division off", None
+        value = updates / (ms * 1e-3)
+        line = {
+            "metric": "Heun-step cell-updates/s (Grid_solver)", "value": value,
+            "unit": "cell-updates/s", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "impl": "reference", "cells_end": n_end,
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s",
+                             "kind": kind, "cores": cores, "sample": sample},
+            "e2e": {"value": value, "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "reference_timing": "best of 3 runs per build, each from the "
+                                "product arm's start state (allocation jitter)",
+            "reference_builds": builds_report,
+        }
+        print(json.dumps(line))
+        return
+
+    # ======================= the product arm ==============================
+    lib = yb.product()
+    assert lib.build_info.startswith("yalla-b200"), lib.build_info
+    assert os.path.realpath(lib.path) == os.path.realpath(os.path.join(
+        ROOT, "yalla_b200", "_lib", "libyalla_b200.so")), lib.path
+    # the product arm's steps make no driver calls NVML could stall: 10 ms
+    sampler = ClockSampler(local_rank, 0.01)
     sim = new_sim(lib, spec, X, types, gs)
-    sim.step(spec["dt"], warmup if not fallback_to_port else 0)
+    sim.step(spec["dt"], warmup)
     sim.sync()
 
     # ---- device-resident throughput ---------------------------------------
     barrier()
     sampler.start()
     ms, updates = sim.step_timed(spec["dt"], steps)
-    repeats = 1
-    if is_reference and not fallback_to_port:
-        # The reference allocates and frees device memory several times per step
-        # (Thrust temporaries); single timings of it scatter by up to 10x on
-        # this pool. Report its BEST of three K-step runs, so that the ratio
-        # the driver computes is the conservative one.
-        repeats = 3
-        for _ in range(repeats - 1):
-            ms_again, updates_again = sim.step_timed(spec["dt"], steps)
-            if updates_again / ms_again > updates / ms:
-                ms, updates = ms_again, updates_again
     barrier()
     clocks = sampler.stop()
     n_end = sim.n()
@@ -460,157 +548,162 @@ def main():
     value = updates / (ms * 1e-3)
 
     # ---- end to end: host buffers through the C ABI ---------------------------
-    # Every step is one independent batch: upload a fresh tissue from pinned host
-    # memory, integrate one step, download the result. Two solver instances on
-    # two streams are double-buffered, so the copies of one batch overlap the
-    # kernels of the other (all of it inside the timed region).
-    e2e = None
-    if not is_reference:
-        sim.close()
-        host_in = torch.from_numpy(X).pin_memory().numpy()
-        n_in = len(host_in)
-        out_cells = min(spec["n_max"], n_in + n_in // 32)  # room for division
-        lanes_out = [torch.zeros((out_cells, lanes), dtype=torch.float32
-                                 ).pin_memory().numpy() for _ in range(2)]
-        counts = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
-        streams = [torch.cuda.Stream() for _ in range(2)]
-        sims = [new_sim(lib, spec, X, types, gs) for _ in range(2)]
-        for one, stream in zip(sims, streams):
-            one.set_stream(stream.cuda_stream)
-        e2e_steps = max(4, steps // 2)
+    # Every step is one independent batch: a tissue is uploaded from pinned host
+    # memory, integrated for one step and downloaded again, all inside the timed
+    # region. yb_sim_step_host_async pipelines the batches through ONE model
+    # instance: two copy streams and two device-side staging slots let the
+    # upload of batch k + 1 and the download of batch k - 1 overlap the kernels
+    # of batch k. Checked afterwards against the same batches run one by one.
+    host_in = torch.from_numpy(X).pin_memory().numpy()
+    n_in = len(host_in)
+    out_cells = min(spec["n_max"], n_in + n_in // 32)  # room for division
+    outs = [torch.zeros((out_cells, lanes), dtype=torch.float32
+                        ).pin_memory().numpy() for _ in range(2)]
+    counts = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+    e2e_steps = max(4, steps // 2)
 
-        def batch(k):
-            i = k % 2
-            streams[i].synchronize()  # the previous batch of this instance
-            sims[i].step_host_async(host_in, spec["dt"], 1, lanes_out[i],
-                                    out_cells, counts[i].data_ptr())
+    def batch(k):
+        sim.step_host_async(host_in, spec["dt"], 1, outs[k % 2], out_cells,
+                            counts[k % 2].data_ptr())
 
-        for k in range(2):
-            batch(k)  # warm both instances (graph capture, RNG set-up)
-        for stream in streams:
-            stream.synchronize()
-        barrier()
-        start = time.perf_counter()
-        for k in range(e2e_steps):
-            batch(k)
-        for stream in streams:
-            stream.synchronize()
-        barrier()
-        seconds = time.perf_counter() - start
-        assert int(counts[0][0]) >= n_in and np.all(np.isfinite(lanes_out[0][:n_in]))
-        cells = n_in * e2e_steps
-        for one in sims:
-            one.close()
-        if use_dist:
-            t = torch.tensor([seconds, float(cells)], dtype=torch.float64,
-                             device="cuda")
-            worst = t.clone()
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            seconds, cells = float(worst[0]), int(t[1])
-        e2e = {"value": cells / seconds, "unit": "cell-updates/s",
-               "h2d_bytes_per_step": n_in * lanes * 4,
-               "d2h_bytes_per_step": out_cells * lanes * 4 + 4,
-               "steps": e2e_steps,
-               "how": "independent batches, 2 solver instances double-buffered "
-                      "on 2 streams, pinned host buffers"}
-        sim = new_sim(lib, spec, X, types, gs)
-
-    # ---- roofline of the dominant kernel (product arm) ---------------------------
-    roofline = None
-    launches_per_step = None
-    if not is_reference:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
-        else:
-            peak, peak_kind = 6650.0, "fallback"
-        sim.step(spec["dt"], 2)
-        sim.profile_sweeps(True)
-        n_before = sim.n()
-        sim.step(spec["dt"], 4)
-        sweep_ms, sweep_launches = sim.read_sweep_profile()
-        n_after = sim.n()
-        sim.profile_sweeps(False)
-        cells_per_launch = 0.5 * (n_before + n_after)
-        # one sweep launch reads state + old velocities and writes dX:
-        # 2 * sizeof(Pt) + 12 bytes per cell (kernels)
-        bytes_per_launch = cells_per_launch * (2 * LANES_BYTES[lanes] + 12)
-        avg_ms = sweep_ms / max(sweep_launches, 1)
-        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "sweep_cubes",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_kind": peak_kind,
-                    "traffic": sweep_traffic(args.workload),
-                    "avg_launch_ms": avg_ms,
-                    "share_of_step": 2 * avg_ms / (ms / steps),
-                    "step_frac": value / world * (9 * LANES_BYTES[lanes] + 36)
-                    / 1e9 / peak,
-                    "note": "instruction-issue bound, not HBM bound; see "
-                            "fp32_issue, DESIGN.md and profiles/"}
-        if rank == 0:
-            # the second ceiling of SURVEY.md 8(d): algorithmic FP32 lane-
-            # instructions per sweep and cell, I = C * 7 + N * (13 + f_pw),
-            # against the microbenchmarked FP32 issue rate of the chip
-            candidates, accepted = pair_statistics(X)
-            per_cell = candidates * 7 + accepted * (
-                13 + FUNCTOR_LANE_INSTR[spec["model"]])
-            fp32_peak = json.load(open(os.path.join(
-                ROOT, "profiles", "r01_microbench_peaks.json")))[
-                    "fp32_lane_instr_per_s_T"] * 1e12
-            fp32_achieved = per_cell * cells_per_launch / (avg_ms * 1e-3)
-            roofline["fp32_issue"] = {
-                "candidates_per_cell": candidates, "accepted_per_cell": accepted,
-                "lane_instr_per_cell_and_sweep": per_cell,
-                "achieved": fp32_achieved / 1e12, "peak": fp32_peak / 1e12,
-                "unit": "T lane-instr/s", "frac": fp32_achieved / fp32_peak,
-                "peak_kind": "microbenchmark (profiles/r01_microbench_peaks.json)"}
-        # kernels of this repo per model step: stage 1 bin_cells, scan_bins,
-        # place_ids, reorder_cells, sweep_cubes, predictor_step; stage 2 the
-        # same minus bin_cells (fused into the predictor), corrector_step
-        # (+ snapshot_count and proliferate in the growth model)
-        launches_per_step = 11 + (2 if spec["model"] == "growth" else 0)
+    if types is not None:
+        sim.set_ints("type", types)
+    sim.set_state(X)       # zero velocities: the batches start from a known state
+    for k in range(2):
+        batch(k)           # warm the pipeline
+    sim.host_drain()
+    barrier()
+    start = time.perf_counter()
+    for k in range(e2e_steps):
+        batch(k)
+    sim.host_drain()
+    barrier()
+    seconds = time.perf_counter() - start
+    last = (e2e_steps - 1) % 2
+    pipelined = outs[last][:n_in].copy()
+    assert int(counts[last][0]) >= n_in and np.all(np.isfinite(pipelined))
+    # the same sequence of batches, one at a time: the cells that existed at the
+    # start of a batch must come out bit-identical (daughters land in slots
+    # chosen by atomics, in either mode)
+    if types is not None:
+        sim.set_ints("type", types)
+    sim.set_state(X)
+    check = np.zeros((spec["n_max"], lanes), dtype=np.float32)
+    for k in range(e2e_steps + 2):
+        sim.step_host(host_in, spec["dt"], 1, check)
+    e2e_verified = bool(np.array_equal(check[:n_in], pipelined))
+    cells = n_in * e2e_steps
+    if use_dist:
+        t = torch.tensor([seconds, float(cells)], dtype=torch.float64,
+                         device="cuda")
+        worst = t.clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        seconds, cells = float(worst[0]), int(t[1])
+    e2e = {"value": cells / seconds, "unit": "cell-updates/s",
+           "h2d_bytes_per_step": n_in * lanes * 4,
+           "d2h_bytes_per_step": out_cells * lanes * 4 + 4,
+           "steps": e2e_steps, "matches_unpipelined_run": e2e_verified,
+           "how": "independent batches pipelined through one model instance: "
+                  "2 copy streams + 2 device staging slots, pinned host buffers"}
     sim.close()
+    sim = new_sim(lib, spec, X, types, gs)
+
+    # ---- roofline of the dominant kernel --------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
+    else:
+        peak, peak_kind = 6650.0, "fallback"
+    sim.step(spec["dt"], 2)
+    sim.profile_sweeps(True)
+    n_before = sim.n()
+    sim.step(spec["dt"], 4)
+    sweep_ms, sweep_launches = sim.read_sweep_profile()
+    n_after = sim.n()
+    sim.profile_sweeps(False)
+    sim.close()
+    cells_per_launch = 0.5 * (n_before + n_after)
+    avg_ms = sweep_ms / max(sweep_launches, 1)
+    # HBM: one sweep launch reads state + old velocities and writes dX:
+    # 2 * sizeof(Pt) + 12 bytes per cell (kernels)
+    bytes_per_launch = cells_per_launch * (2 * LANES_BYTES[lanes] + 12)
+    hbm_achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    hbm = {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s",
+           "frac": hbm_achieved / peak, "peak_kind": peak_kind,
+           "algorithmic_bytes_per_launch": bytes_per_launch,
+           "step_frac": value / world * (9 * LANES_BYTES[lanes] + 36) / 1e9 / peak}
+    roofline = None
+    if rank == 0:
+        # The binding ceiling: algorithmic FP32 lane-instructions
+        # per sweep and cell, I = C * 7 + N * (13 + f_pw), against the
+        # microbenchmarked FP32 issue rate of the chip. The HBM figure is
+        # reported next to it: this path is not bandwidth bound.
+        candidates, accepted = pair_statistics(X)
+        per_cell = candidates * 7 + accepted * (
+            13 + FUNCTOR_LANE_INSTR[spec["model"]])
+        fp32_peak = json.load(open(os.path.join(
+            ROOT, "profiles", "r01_microbench_peaks.json")))[
+                "fp32_lane_instr_per_s_T"]
+        fp32_achieved = per_cell * cells_per_launch / (avg_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp32_issue", "kernel": "sweep_cubes",
+            "achieved": fp32_achieved, "peak": fp32_peak,
+            "unit": "T lane-instr/s", "frac": fp32_achieved / fp32_peak,
+            "peak_kind": "microbenchmark (profiles/r01_microbench_peaks.json)",
+            "candidates_per_cell": candidates, "accepted_per_cell": accepted,
+            "lane_instr_per_cell_and_sweep": per_cell,
+            "traffic": sweep_traffic(args.workload),
+            "avg_launch_ms": avg_ms,
+            "share_of_step": 2 * avg_ms / (ms / steps),
+            "hbm": hbm,
+            "note": "the sweep is instruction-issue / latency bound, not HBM "
+                    "bound (DESIGN.md section 3); both ceilings are reported"}
+
+    # ---- the same N GPUs on ONE tissue: the slab-decomposed sphere ---------------
+    # (configs[4]: 12.5 M float3 cells per GPU, 100 M at 8 GPUs; on one GPU also
+    # the whole 100 M-cell sphere, the T1 of the strong-scaling figure)
+    decomposed = None
+    if not args.no_decomposed:
+        dd_spec = DD_WORKLOADS["sphere_dd"]
+        dd_steps = max(3, min(steps, 10))
+        record = run_decomposed(dd_steps, 3, dd_spec, "sphere_dd", rank,
+                                local_rank, world, e2e=False)
+        if rank == 0:
+            decomposed = {key: record[key] for key in (
+                "value", "unit", "n_gpus", "steps", "ms_per_step", "ghost_cells",
+                "problems", "config")}
+            decomposed["sweep_ms_per_launch"] = record["roofline"]["avg_launch_ms"]
+        if world == 1 and os.environ.get("YALLA_BENCH_STRONG", "1") != "0":
+            whole = run_decomposed(3, 3, dd_spec, "sphere_dd", 0, local_rank, 1,
+                                   cells_total=100_000_000, e2e=False)
+            decomposed["whole_sphere_on_one_gpu"] = {
+                key: whole[key] for key in ("value", "ms_per_step", "steps", "config")}
 
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
         return
 
+    # kernels of this repo per model step: stage 1 bin_cells, scan_bins,
+    # place_ids, reorder_cells, sweep_cubes, predictor_step; stage 2 the same
+    # minus bin_cells (fused into the predictor), corrector_step; models with a
+    # counter reset add zero_cells per stage, the growth model snapshot_count
+    # and proliferate
+    launches_per_step = 11 + {"growth": 4, "branching": 2}.get(spec["model"], 0)
     line = {
         "metric": "Heun-step cell-updates/s (Grid_solver)",
-        "value": value, "unit": "cell-updates/s", "n_gpus": world if not
-        is_reference else 1, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": spec["model"],
-                   "cells_start": spec["n"], "cells_end": n_end,
-                   "n_max": spec["n_max"], "grid_size": gs, "dt": spec["dt"],
-                   "tissue": "jittered FCC ball, shuffled order, seeded",
-                   "replicas": world if not is_reference else 1,
-                   "l2": "working set (>300 MB per replica) exceeds the 126 MB L2"},
-        "clocks": clocks,
+        "value": value, "unit": "cell-updates/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
+        "clocks": clocks, "cells_end": n_end, "cpus": cpus,
+        "e2e": e2e, "roofline": roofline,
+        "gpu_launches": launches_per_step * steps * world,  # all ranks
+        "decomposed": decomposed,
     }
-    if is_reference:
-        line["impl"] = "reference"
-        kind = "port" if fallback_to_port else "reference"
-        line["cpu_baseline"] = {
-            "value": value, "unit": "cell-updates/s", "kind": kind,
-            "cores": (os.cpu_count() if fallback_to_port else 0),
-            "sample": ("CPU oracle port, division off" if fallback_to_port else
-                       "the reference's own CUDA build (unmodified headers, "
-                       "sm_100a) on the full workload; ya||a has no CPU path")}
-        line["e2e"] = {"value": value, "unit": "cell-updates/s",
-                       "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-        line["gpu_launches"] = 0
-        line["config"]["reference_timing"] = (
-            f"best of {repeats} runs of {steps} steps (allocation jitter)")
-    else:
-        line["e2e"] = e2e
-        line["roofline"] = roofline
-        line["gpu_launches"] = launches_per_step * steps * world  # all ranks
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(spec)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(spec)
     print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()

@@ -153,9 +153,10 @@ public:
 
 protected:
     // both knobs are baked into captured graphs
-    float graph_key() const
+    yb::Graph_key graph_key() const
     {
-        return this->cube_size * 4096.f + gabriel_coefficient;
+        return yb::Graph_key{this->cube_size, gabriel_coefficient, this->z_half,
+            this->active_cubes};
     }
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,

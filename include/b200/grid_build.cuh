@@ -33,6 +33,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <functional>
+#include <vector>
 
 #include "../cudebug.cuh"
 #include "layout.cuh"
@@ -62,7 +64,8 @@ struct Step_ctl {
     int sweep_blocks_done;  // last-block election in the pairwise sweep
     int out_of_grid;      // cells whose cube id had to be clamped (diagnostic)
     int n_snapshot;       // n used by the step in flight (diagnostic)
-    int pad0, pad1;
+    int list_overflow;    // a neighbour list of the split sweep was too short
+    int pad1;
     float drift[2][4];    // per Heun stage: mean (or fixed-point) dX.xyz
     // Domain decomposition (b200/slab.cuh): cells with an id >= n_owned are
     // ghosts -- neighbours only; in force while external_drift is set.
@@ -73,11 +76,31 @@ struct Step_ctl {
 };
 
 // Set by the solver around the generic-forces callback, so that forces called
-// from it know how many cells there are and which stream the step runs on.
+// from it (link_forces, wall_forces, ...) know how many cells there are, which
+// stream the step runs on, and whether their launches are being recorded into
+// a CUDA graph.
+//
+// A step with generic forces can only be replayed from a graph if the forces
+// are "capturable" (Heun_solver::capture_generic_forces): they enqueue the same
+// work on `stream` every time and take the live cell count from d_n_cells --
+// n_cells is then n_max_cells, an upper bound. Work that must NOT be recorded
+// (rebuilding a cache, allocating) goes to eager_stream, the stream the graph
+// is launched on afterwards; a force may register a hook that runs on that
+// stream before every replay and returns false if the recorded launches are
+// no longer valid (the graph is then captured again).
+using Replay_hook = std::function<bool(cudaStream_t)>;
+
 struct Stage_context {
     int n_cells;
     int n_max_cells;
     cudaStream_t stream;
+    const int* d_n_cells = nullptr;  // live count in device memory
+    int stage = 0;                   // Heun stage: 0 predictor, 1 corrector
+    bool capturing = false;
+    const void* solver = nullptr;    // with step_serial: identifies the step
+    unsigned long long step_serial = 0;
+    cudaStream_t eager_stream = 0;
+    std::vector<Replay_hook>* hooks = nullptr;
 };
 
 inline Stage_context*& current_stage()

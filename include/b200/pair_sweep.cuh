@@ -330,6 +330,7 @@ __device__ __forceinline__ void finish_drift(float3 my_partial,
                 d_dX, stage, ctl);
         }
         ctl->sweep_blocks_done = 0;
+        ctl->list_overflow = 0;  // (the fused kernel just took the stage over)
     }
 }
 
@@ -345,9 +346,11 @@ __global__ void __launch_bounds__(
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
     const int* __restrict__ offset, float cube_size, int grid_size, int z_half,
     int n_cubes, Pt* d_dX, float* __restrict__ partials, int stage,
-    int drift_mode, int fix_point, Step_ctl* ctl)
+    int drift_mode, int fix_point, Step_ctl* ctl, int only_if_overflow)
 {
     using L = Layout<Pt>;
+    // behind list_cubes + interact_lists: only if a neighbour list overflowed
+    if (only_if_overflow && *(volatile int*)&ctl->list_overflow == 0) return;
     constexpr int SWEEP_STAGE_CAP = Sweep_config<L::lanes>::stage_cap;
     constexpr int SWEEP_LIST_CAP = Sweep_config<L::lanes>::list_cap;
     extern __shared__ __align__(16) unsigned char sweep_smem[];
@@ -554,6 +557,274 @@ __global__ void __launch_bounds__(
         cta_sum.x += chunk_sum.x, cta_sum.y += chunk_sum.y, cta_sum.z += chunk_sum.z;
     }
 
+    finish_drift<SWEEP_THREADS>(cta_sum, partials, n, stage, drift_mode,
+        fix_point, d_dX, ctl, s_red);
+}
+
+
+// ---- Grid solver sweep in two kernels, for points with extra lanes --------------
+// Heavy functors (polarity forces, functors that gather their own per-cell
+// arrays) spend the sweep waiting: on dependent memory round trips of the user
+// code and on long FMA/XU chains. What hides that is more warps in flight and
+// more L1, and the fused kernel above has neither to give -- its registers hold
+// the scan state next to the functor's, and its staging windows take most of
+// the SM's shared memory/L1. So for these point types the two phases run as two
+// kernels:
+//
+//   list_cubes      phase 1 alone (no Pt, no functor: ONE instantiation for all
+//                   models): the staged candidate scan, whose survivors are
+//                   written to a neighbour list in global memory -- row e of
+//                   nb[] holds the e-th listed slot of every cell (entry-major,
+//                   so the lanes of a warp read and write consecutive words);
+//   interact_lists  phase 2 alone: one thread per cell walks its list in order
+//                   (the reference's order), gathers the partner from the
+//                   cube-ordered planes through L1, exact cut-off, functor,
+//                   friction, epilogue. No shared memory to speak of, so nearly
+//                   the whole 256 KB of the SM is L1 for those gathers and for
+//                   the functor's own, and the register budget is the functor's.
+//
+// A cell with more than LIST_MAX listed candidates (crowded tissues) raises
+// Step_ctl::list_overflow; interact_lists then leaves the stage to the fused
+// kernel, which is always launched behind it and returns at once otherwise.
+constexpr int LIST_MAX = 64;
+
+struct List_config {  // list_cubes: the float3 budget of the fused sweep
+    static constexpr int stage_cap = 1024;
+    static constexpr int list_cap = 24;
+    static constexpr int min_ctas = 8;
+    static constexpr size_t smem =
+        size_t(stage_cap) * sizeof(float4) +
+        size_t(SWEEP_ROWS) * SWEEP_THREADS * sizeof(uint32_t) +
+        size_t(list_cap) * SWEEP_THREADS * sizeof(uint16_t);
+};
+
+__global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
+    list_cubes(const int* __restrict__ d_n, int n_max,
+        const float4* __restrict__ pos4, const int* __restrict__ cube_sorted,
+        const int* __restrict__ offset, float cube_size, int grid_size,
+        int z_half, int n_cubes, int* __restrict__ nb,
+        int* __restrict__ nb_count, int nb_stride, Step_ctl* ctl)
+{
+    constexpr int SWEEP_STAGE_CAP = List_config::stage_cap;
+    constexpr int SWEEP_LIST_CAP = List_config::list_cap;
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    float4* s_pos = reinterpret_cast<float4*>(sweep_smem);
+    uint32_t* s_range = reinterpret_cast<uint32_t*>(s_pos + SWEEP_STAGE_CAP);
+    uint16_t* s_list =
+        reinterpret_cast<uint16_t*>(s_range + SWEEP_ROWS * SWEEP_THREADS);
+    __shared__ int s_row_lo[SWEEP_ROWS];
+    __shared__ int s_row_v[SWEEP_ROWS + 1];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int t = threadIdx.x;
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, SWEEP_THREADS);
+    const float reach2 = cube_size * cube_size * SWEEP_PREFILTER_SLACK;
+    const int n_owned = ctl->external_drift ? ctl->n_owned : n_max;
+
+    if (t == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int first_slot = chunk * SWEEP_THREADS;
+        const int k = first_slot + t;
+        const bool live = k < n;
+
+        if (t < SWEEP_ROWS) {
+            const int last_slot = min(first_slot + SWEEP_THREADS, n) - 1;
+            const int shift = row_shift(t, grid_size);
+            const int lo = __ldg(offset +
+                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, n_cubes));
+            const int hi = __ldg(offset +
+                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, n_cubes));
+            s_row_lo[t] = lo;
+            s_row_v[t + 1] = hi > lo ? hi - lo : 0;
+        }
+        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+        int my_cube = 0;
+        if (live) {
+            me = __ldg(pos4 + k);
+            my_cube = __ldg(cube_sorted + k);
+        }
+        float gap2[3][3];
+        trim_gaps(me, cube_size, grid_size, z_half, my_cube, gap2);
+        int my_lo[SWEEP_ROWS], my_hi[SWEEP_ROWS];
+#pragma unroll
+        for (int r = 0; r < SWEEP_ROWS; r++) {
+            const int c = my_cube + row_shift(r, grid_size);
+            const float row_gap2 = gap2[1][r % 3] + gap2[2][r / 3];
+            const bool row_out = !live || row_gap2 >= SWEEP_TRIM_LIMIT;
+            const int first = row_gap2 + gap2[0][1] >= SWEEP_TRIM_LIMIT ? c : c - 1;
+            const int last = row_gap2 + gap2[0][2] >= SWEEP_TRIM_LIMIT ? c + 1 : c + 2;
+            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, n_cubes));
+            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, n_cubes));
+        }
+        __syncthreads();
+        if (t == 0) {
+            int v = 0;
+            s_row_v[0] = 0;
+#pragma unroll
+            for (int r = 0; r < SWEEP_ROWS; r++) {
+                v += s_row_v[r + 1];
+                s_row_v[r + 1] = v;
+            }
+        }
+        __syncthreads();
+        const int total = s_row_v[SWEEP_ROWS];
+        const bool owned = live && __float_as_int(me.w) < n_owned;
+        int n_listed = 0;
+
+        for (int v0 = 0; v0 < total; v0 += SWEEP_STAGE_CAP) {
+            if (v0 > 0) __syncthreads();
+            if (t == 0) {
+                const int v1 = min(v0 + SWEEP_STAGE_CAP, total);
+                mbar_expect_tx(&s_bar, uint32_t(v1 - v0) * sizeof(float4));
+#pragma unroll 1
+                for (int r = 0; r < SWEEP_ROWS; r++) {
+                    const int a = max(s_row_v[r], v0);
+                    const int b = min(s_row_v[r + 1], v1);
+                    if (b > a)
+                        bulk_g2s(s_pos + (a - v0),
+                            pos4 + (s_row_lo[r] + (a - s_row_v[r])),
+                            uint32_t(b - a) * sizeof(float4), &s_bar);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < SWEEP_ROWS; r++) {
+                const int base = s_row_v[r] - s_row_lo[r] - v0;
+                const int a = min(max(my_lo[r] + base, 0), SWEEP_STAGE_CAP);
+                const int b = min(max(my_hi[r] + base, a), SWEEP_STAGE_CAP);
+                s_range[r * SWEEP_THREADS + t] = uint32_t(a) | (uint32_t(b) << 16);
+            }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1u;
+
+            const uint32_t list_begin = smem_u32(s_list + t);
+            const uint32_t list_full =
+                list_begin + SWEEP_LIST_CAP * SWEEP_THREADS * sizeof(uint16_t);
+            int r = 0;
+            uint32_t range = owned ? s_range[t] : 0u;
+            int a = int(range & 0xffffu), b = int(range >> 16);
+            while (true) {
+                uint32_t la = list_begin;
+                while (true) {
+                    const float4* pp = s_pos + a;
+                    uint32_t entry = (uint32_t(r) << 12) | uint32_t(a);
+                    const uint32_t entry_end = entry + uint32_t(b - a);
+#pragma unroll 2
+                    for (; entry < entry_end && la != list_full; entry++, pp++) {
+                        const float4 p = *pp;
+                        const float dx = me.x - p.x, dy = me.y - p.y,
+                                    dz = me.z - p.z;
+                        const float d2 = dx * dx + dy * dy + dz * dz;
+                        if (!(d2 > reach2)) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(la),
+                                         "h"(uint16_t(entry))
+                                         : "memory");
+                            la += SWEEP_THREADS * sizeof(uint16_t);
+                        }
+                    }
+                    a = int(entry & 4095u);
+                    if (__any_sync(0xffffffffu, a < b)) break;  // list(s) full
+                    ++r;
+                    range = owned && r < SWEEP_ROWS
+                                ? s_range[r * SWEEP_THREADS + t]
+                                : 0u;
+                    a = int(range & 0xffffu), b = int(range >> 16);
+                    if (r == SWEEP_ROWS) break;
+                }
+                // flush: the e-th entry of every lane goes to row n_listed + e
+                const int listed = listed_at(la, list_begin);
+                for (int e = 0; e < listed; e++) {
+                    const unsigned entry = s_list[e * SWEEP_THREADS + t];
+                    const int row = entry >> 12, at = entry & 4095;
+                    const int kj = s_row_lo[row] + (v0 + at - s_row_v[row]);
+                    if (n_listed + e < LIST_MAX)
+                        nb[size_t(n_listed + e) * nb_stride + k] = kj;
+                }
+                n_listed += listed;
+                if (r == SWEEP_ROWS) break;
+            }
+        }
+        if (live) nb_count[k] = n_listed;
+        if (n_listed > LIST_MAX) ctl->list_overflow = 1;
+    }
+}
+
+#ifndef YB_INTERACT_CTAS
+#define YB_INTERACT_CTAS 8
+#endif
+
+template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
+    float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
+__global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_lists(
+    const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
+    const float4* __restrict__ aux, const int* __restrict__ nb,
+    const int* __restrict__ nb_count, int nb_stride, float cube_size, Pt* d_dX,
+    float* __restrict__ partials, int stage, int drift_mode, int fix_point,
+    Step_ctl* ctl)
+{
+    using L = Layout<Pt>;
+    __shared__ float s_red[3][SWEEP_THREADS / 32];
+    // crowded: the fused kernel behind this one takes the stage
+    if (*(volatile int*)&ctl->list_overflow) return;
+
+    const int t = threadIdx.x;
+    const int n = live_cells(d_n, n_max);
+    const int n_chunks = ceil_div(n, SWEEP_THREADS);
+    const int n_owned = ctl->external_drift ? ctl->n_owned : n_max;
+    float3 my_sum{0.f, 0.f, 0.f};  // this thread's cells, chunk after chunk
+
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int k = chunk * SWEEP_THREADS + t;
+        if (k >= n) continue;
+        const float4 me = __ldg(pos4 + k);
+        const int my_id = __float_as_int(me.w);
+        if (my_id >= n_owned) continue;  // ghost: a partner, never a subject
+        const Pt Xi = assemble_pt<Pt>(me, aux + size_t(k) * L::aux_vec4);
+        const int count = min(__ldg(nb_count + k), LIST_MAX);
+        Pt F{0};
+        float3 sum_v{0.f, 0.f, 0.f};
+        float sum_friction = 0.f;
+
+        const int* my_nb = nb + k;
+        for (int e = 0; e < count; e++) {
+            const int kj = __ldg(my_nb + size_t(e) * nb_stride);
+            const float4* aux_j = aux + size_t(kj) * L::aux_vec4;
+            const float3 vj = velocity_of<Pt>(aux_j);
+            const float4 pj = __ldg(pos4 + kj);
+            const Pt Xj = assemble_pt<Pt>(pj, aux_j);
+            const Pt rij = Xi - Xj;
+            const float dist = norm3df(rij.x, rij.y, rij.z);
+            if (dist >= cube_size) continue;
+
+            const int j_id = __float_as_int(pj.w);
+            F += pw_int(Xi, rij, dist, my_id, j_id);
+            const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
+            sum_friction += friction;
+            if (friction != 0.f) sum_v += friction * vj;
+        }
+
+        Pt dX = F;
+        if (SEEDED) {
+            dX = load_pt_rw(d_dX, my_id);
+            dX += F;
+        }
+        if (sum_friction > 0) {
+            dX.x += sum_v.x / sum_friction;
+            dX.y += sum_v.y / sum_friction;
+            dX.z += sum_v.z / sum_friction;
+        }
+        store_pt(d_dX, my_id, dX);
+        my_sum.x += dX.x, my_sum.y += dX.y, my_sum.z += dX.z;
+    }
+
+    // one deterministic CTA-wide sum at the end (chunks are dealt in a fixed
+    // order, so every thread's running sum is reproducible)
+    __syncthreads();
+    const float3 cta_sum =
+        block_sum3<SWEEP_THREADS>(my_sum.x, my_sum.y, my_sum.z, s_red);
     finish_drift<SWEEP_THREADS>(cta_sum, partials, n, stage, drift_mode,
         fix_point, d_dX, ctl, s_red);
 }

@@ -11,15 +11,20 @@
 // (links.cuh:99-125) and reads the link count back to the host twice per call.
 // Here, when called from inside a solver step (the normal case: it is passed
 // as, or from, the generic-forces callback), the sum is an atomic-free
-// segmented reduction:
-//   1. bin_link_ends    bucket both ends of every live link by cell id
-//   2. scan_bins        per-cell offsets (same single-pass scan as the grid)
-//   3. place_link_ends  write (2 * link + side) entries into the cell's segment
-//   4. pull_on_cells    one thread per cell adds its entries' forces in
-//                       ascending link order and updates d_dX once.
-// The link count stays on the device and the result no longer depends on the
-// order in which atomics happen to land. Custom Link_force functors do their
-// own (atomic) updates, exactly as in the reference.
+// segmented reduction over a per-cell index of the link ends (a CSR):
+//   build   bin_link_ends      bucket both ends of every live link by cell id
+//           scan_bins          per-cell offsets (the grid's single-pass scan)
+//           place_link_ends    (2 * link + side) entries into the cell's segment
+//           order_link_ends    every segment into ascending link order (hubs,
+//           order_hub_segments  cells with > 32 ends, by one CTA each)
+//   pull    pull_on_cells      one thread per cell adds its entries' forces in
+//           pull_on_hubs       ascending link order and updates d_dX once.
+// The index is built once per step (the second Heun stage reuses the first
+// stage's) or, with Links::cache_topology, once per change of the links. All
+// counts stay on the device, every launch is capturable into a CUDA graph, and
+// the result does not depend on the order in which atomics happen to land.
+// Custom Link_force functors do their own (atomic) updates, exactly as in the
+// reference.
 #pragma once
 
 #include <assert.h>
@@ -27,6 +32,7 @@
 #include <stdlib.h>
 #include <time.h>
 #include <functional>
+#include <memory>
 
 #include "b200/grid_build.cuh"
 #include "b200/layout.cuh"
@@ -57,6 +63,78 @@ inline int wall_clock_seed()
 }  // namespace yb
 
 
+namespace yb {
+
+// Per-cell index of the link ends (internal). Shared between the Links object
+// and the replay hooks of captured steps, so it can outlive either.
+struct Link_segments {
+    int cell_capacity = 0;
+    int n_tiles = 0;
+    int* count = nullptr;    // per cell, zero between builds
+    int* offset = nullptr;   // per cell (+1, + padding)
+    int* arrival = nullptr;  // 2 per link (scratch of the hub sort afterwards)
+    int* entry = nullptr;    // 2 per link: 2 * link + side, grouped by cell
+    int* hubs = nullptr;     // cells with more than LINK_HUB ends
+    int* hub_ctl = nullptr;  // [0] number of hubs, [1] links with a bad end
+    unsigned long long* status = nullptr;
+    Step_ctl* ctl = nullptr;
+    // bookkeeping of the cache
+    bool owner_alive = true;
+    bool dirty = true;              // d_link changed since the last build
+    const void* built_by = nullptr;  // solver + step of the last build
+    unsigned long long built_in_step = 0;
+
+    Link_segments() = default;
+    Link_segments(const Link_segments&) = delete;
+    Link_segments& operator=(const Link_segments&) = delete;
+    ~Link_segments() { release(); }
+
+    void reserve(int n_cells, int n_links_max)
+    {
+        if (n_cells <= cell_capacity) return;
+        release();
+        const size_t bins = static_cast<size_t>(scan_padded(n_cells + 1));
+        const size_t ends = 2 * static_cast<size_t>(n_links_max > 0 ? n_links_max : 1);
+        cell_capacity = n_cells;
+        n_tiles = static_cast<int>(bins / SCAN_TILE);
+        YB_CUDA(cudaMalloc(&count, bins * sizeof(int)));
+        YB_CUDA(cudaMemset(count, 0, bins * sizeof(int)));
+        YB_CUDA(cudaMalloc(&offset, bins * sizeof(int)));
+        YB_CUDA(cudaMalloc(&arrival, ends * sizeof(int)));
+        YB_CUDA(cudaMalloc(&entry, ends * sizeof(int)));
+        // a hub has more than LINK_HUB = 32 ends, so there are fewer than
+        // ends / 32 of them: the list cannot overflow
+        YB_CUDA(cudaMalloc(&hubs, (ends / 32 + 1) * sizeof(int)));
+        YB_CUDA(cudaMalloc(&hub_ctl, 4 * sizeof(int)));
+        YB_CUDA(cudaMemset(hub_ctl, 0, 4 * sizeof(int)));
+        YB_CUDA(cudaMalloc(&status, n_tiles * sizeof(unsigned long long)));
+        YB_CUDA(cudaMemset(status, 0, n_tiles * sizeof(unsigned long long)));
+        YB_CUDA(cudaMalloc(&ctl, sizeof(Step_ctl)));
+        Step_ctl fresh{};
+        fresh.scan_epoch = 1;
+        YB_CUDA(cudaMemcpy(ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        dirty = true;
+        built_by = nullptr;
+    }
+    void release()
+    {
+        cudaFree(ctl);
+        cudaFree(status);
+        cudaFree(hub_ctl);
+        cudaFree(hubs);
+        cudaFree(entry);
+        cudaFree(arrival);
+        cudaFree(offset);
+        cudaFree(count);
+        ctl = nullptr, status = nullptr, hub_ctl = nullptr, hubs = nullptr;
+        entry = nullptr, arrival = nullptr, offset = nullptr, count = nullptr;
+        cell_capacity = 0;
+    }
+};
+
+}  // namespace yb
+
+
 class Links {
 public:
     Link* h_link;
@@ -68,7 +146,8 @@ public:
     float strength;
 
     Links(int n_max, float strength = 1.f / 5)
-        : n_max{n_max}, strength{strength}
+        : n_max{n_max}, strength{strength},
+          segments{std::make_shared<yb::Link_segments>()}
     {
         const size_t links = static_cast<size_t>(n_max > 0 ? n_max : 1);
         h_link = static_cast<Link*>(malloc(links * sizeof(Link)));
@@ -87,7 +166,7 @@ public:
     Links& operator=(const Links&) = delete;
     ~Links()
     {
-        release_segments();
+        segments->owner_alive = false;  // captured steps notice and re-capture
         cudaFree(d_state);
         cudaFree(d_n);
         cudaFree(d_link);
@@ -99,6 +178,7 @@ public:
     {
         assert(n <= n_max);
         YB_CUDA(cudaMemcpy(d_n, &n, sizeof(int), cudaMemcpyHostToDevice));
+        mark_changed();
     }
     int get_d_n()
     {
@@ -122,6 +202,7 @@ public:
         YB_CUDA(cudaMemcpy(d_link, h_link,
             static_cast<size_t>(n_max) * sizeof(Link), cudaMemcpyHostToDevice));
         YB_CUDA(cudaMemcpy(d_n, h_n, sizeof(int), cudaMemcpyHostToDevice));
+        mark_changed();
     }
     void copy_to_host()
     {
@@ -131,53 +212,26 @@ public:
         assert(*h_n <= n_max);
     }
 
-    // ---- scratch of the segmented reduction (internal) ----------------------
-    struct Segments {
-        int cell_capacity = 0;
-        int n_tiles = 0;
-        int* count = nullptr;    // per cell, zero between calls
-        int* offset = nullptr;   // per cell (+1, + padding)
-        int* arrival = nullptr;  // 2 per link
-        int* entry = nullptr;    // 2 per link: 2 * link + side, by cell
-        unsigned long long* status = nullptr;
-        yb::Step_ctl* ctl = nullptr;
-    } segments;
+    // Extension: by default link_forces re-indexes the links once per solver
+    // step, because model kernels rewire d_link on the device between steps.
+    // With cache_topology = true the index is kept until the links change
+    // through copy_to_device / set_d_n / reset or the model says so with
+    // mark_changed() (e.g. after its own rewiring kernel).
+    bool cache_topology = false;
+    void mark_changed() { segments->dirty = true; }
 
-    void reserve_segments(int n_cells)
+    // Extension: links with an end outside [0, n_max of the cells) seen by the
+    // last link_forces call inside a step (they are skipped). Blocks.
+    int links_out_of_range()
     {
-        if (n_cells <= segments.cell_capacity) return;
-        release_segments();
-        const size_t bins = static_cast<size_t>(yb::scan_padded(n_cells + 1));
-        const size_t ends = 2 * static_cast<size_t>(n_max > 0 ? n_max : 1);
-        segments.cell_capacity = n_cells;
-        segments.n_tiles = static_cast<int>(bins / yb::SCAN_TILE);
-        YB_CUDA(cudaMalloc(&segments.count, bins * sizeof(int)));
-        YB_CUDA(cudaMemset(segments.count, 0, bins * sizeof(int)));
-        YB_CUDA(cudaMalloc(&segments.offset, bins * sizeof(int)));
-        YB_CUDA(cudaMalloc(&segments.arrival, ends * sizeof(int)));
-        YB_CUDA(cudaMalloc(&segments.entry, ends * sizeof(int)));
-        YB_CUDA(cudaMalloc(&segments.status,
-            segments.n_tiles * sizeof(unsigned long long)));
-        YB_CUDA(cudaMemset(segments.status, 0,
-            segments.n_tiles * sizeof(unsigned long long)));
-        YB_CUDA(cudaMalloc(&segments.ctl, sizeof(yb::Step_ctl)));
-        yb::Step_ctl fresh{};
-        fresh.scan_epoch = 1;
-        YB_CUDA(cudaMemcpy(
-            segments.ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        if (segments->hub_ctl == nullptr) return 0;
+        int bad = 0;
+        YB_CUDA(cudaMemcpy(&bad, segments->hub_ctl + 1, sizeof(int),
+            cudaMemcpyDeviceToHost));
+        return bad;
     }
 
-private:
-    void release_segments()
-    {
-        cudaFree(segments.ctl);
-        cudaFree(segments.status);
-        cudaFree(segments.entry);
-        cudaFree(segments.arrival);
-        cudaFree(segments.offset);
-        cudaFree(segments.count);
-        segments = Segments{};
-    }
+    std::shared_ptr<yb::Link_segments> segments;  // internal
 };
 
 
@@ -224,23 +278,34 @@ __global__ void link(const Pt* __restrict__ d_X, Pt* d_dX,
 
 namespace yb {
 
-// 1. count the live ends per cell and remember each end's arrival rank
+constexpr int LINK_HUB = 32;        // segments longer than this go to one CTA each
+constexpr int LINK_HUB_THREADS = 256;
+constexpr int LINK_HUB_SORT = 4096;  // entries a CTA sorts in shared memory
+
+// build 1: count the ends per cell and remember each end's arrival rank. Like
+// the reference's kernel, every link with a != b pulls; a link with an end
+// outside the cell arrays is skipped and counted (the reference would write
+// out of bounds).
 __global__ void __launch_bounds__(256) bin_link_ends(
     const Link* __restrict__ d_link, const int* __restrict__ d_n_links,
-    int n_links_max, int n_cells, int* count, int* __restrict__ arrival)
+    int n_links_max, int n_cells_max, int* count, int* __restrict__ arrival,
+    int* hub_ctl)
 {
     const int n_links = live_cells(d_n_links, n_links_max);
+    if (blockIdx.x == 0 && threadIdx.x == 0) hub_ctl[0] = 0;  // no hubs yet
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n_links;
          l += gridDim.x * blockDim.x) {
         const int a = d_link[l].a, b = d_link[l].b;
-        const bool active = a != b && a >= 0 && b >= 0 && a < n_cells &&
-                            b < n_cells;
+        const bool in_range = a >= 0 && b >= 0 && a < n_cells_max &&
+                              b < n_cells_max;
+        if (a != b && !in_range) atomicAdd(hub_ctl + 1, 1);
+        const bool active = a != b && in_range;
         arrival[2 * l] = active ? atomicAdd(count + a, 1) : -1;
         arrival[2 * l + 1] = active ? atomicAdd(count + b, 1) : -1;
     }
 }
 
-// 3. entries of a cell, in arrival order
+// build 3: entries of a cell, in arrival order
 __global__ void __launch_bounds__(256) place_link_ends(
     const Link* __restrict__ d_link, const int* __restrict__ d_n_links,
     int n_links_max, const int* __restrict__ offset,
@@ -256,66 +321,239 @@ __global__ void __launch_bounds__(256) place_link_ends(
     }
 }
 
-// 4. one thread per cell: visit its entries by ascending link index (repeated
-//    minimum search -- segments hold a handful of entries) and add
-//    -/+ strength * r / |r| for the a / b end, like linear_force does.
+// build 4: ascending link order inside every segment, so that the sums below
+// are accumulated in an order that does not depend on atomic timing. Short
+// segments (a handful of entries) by insertion sort, one thread each; long
+// ones are listed for order_hub_segments.
+__global__ void __launch_bounds__(256) order_link_ends(int n_cells_max,
+    const int* __restrict__ offset, int* entry, int* __restrict__ hubs,
+    int* hub_ctl)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells_max;
+         c += gridDim.x * blockDim.x) {
+        const int start = __ldg(offset + c), end = __ldg(offset + c + 1);
+        const int m = end - start;
+        if (m < 2) continue;
+        if (m > LINK_HUB) {
+            hubs[atomicAdd(hub_ctl, 1)] = c;
+            continue;
+        }
+        for (int k = start + 1; k < end; k++) {
+            const int e = entry[k];
+            int q = k - 1;
+            while (q >= start && entry[q] > e) {
+                entry[q + 1] = entry[q];
+                q--;
+            }
+            entry[q + 1] = e;
+        }
+    }
+}
+
+// build 5: one CTA per hub. Up to LINK_HUB_SORT entries are sorted in shared
+// memory (bitonic); longer segments by ranking every entry against all others
+// into the (by now unused) arrival array and copying back.
+__global__ void __launch_bounds__(LINK_HUB_THREADS) order_hub_segments(
+    const int* __restrict__ offset, int* entry, int* scratch,
+    const int* __restrict__ hubs, const int* __restrict__ hub_ctl)
+{
+    __shared__ int s_e[LINK_HUB_SORT];
+    const int n_hubs = hub_ctl[0];
+    for (int h = blockIdx.x; h < n_hubs; h += gridDim.x) {
+        const int c = hubs[h];
+        const int start = offset[c], m = offset[c + 1] - start;
+        if (m <= LINK_HUB_SORT) {
+            int padded = 1;
+            while (padded < m) padded <<= 1;
+            for (int q = threadIdx.x; q < padded; q += blockDim.x)
+                s_e[q] = q < m ? entry[start + q] : 0x7fffffff;
+            __syncthreads();
+            for (int k = 2; k <= padded; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int q = threadIdx.x; q < padded; q += blockDim.x) {
+                        const int partner = q ^ j;
+                        if (partner > q) {
+                            const bool up = (q & k) == 0;
+                            const int x = s_e[q], y = s_e[partner];
+                            if ((x > y) == up) s_e[q] = y, s_e[partner] = x;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int q = threadIdx.x; q < m; q += blockDim.x)
+                entry[start + q] = s_e[q];
+        } else {
+            for (int q = threadIdx.x; q < m; q += blockDim.x) {
+                const int e = entry[start + q];
+                int rank = 0;
+                for (int p = 0; p < m; p++) rank += entry[start + p] < e;
+                scratch[start + rank] = e;  // entries are distinct
+            }
+            __syncthreads();
+            for (int q = threadIdx.x; q < m; q += blockDim.x)
+                entry[start + q] = scratch[start + q];
+        }
+        __syncthreads();
+    }
+}
+
+// -/+ strength * r / |r| on the a / b end of the link, like linear_force.
 template<typename Pt>
-__global__ void __launch_bounds__(128) pull_on_cells(int n_cells,
+__device__ __forceinline__ void add_link_pull(const Pt* __restrict__ d_X,
+    const Link* __restrict__ d_link, int e, float strength, float& fx,
+    float& fy, float& fz)
+{
+    const Link l = d_link[e >> 1];
+    const Pt r = load_pt(d_X, l.a) - load_pt(d_X, l.b);
+    const float dist = norm3df(r.x, r.y, r.z);
+    if (e & 1) {  // this cell is the b end
+        fx += strength * r.x / dist;
+        fy += strength * r.y / dist;
+        fz += strength * r.z / dist;
+    } else {
+        fx += -strength * r.x / dist;
+        fy += -strength * r.y / dist;
+        fz += -strength * r.z / dist;
+    }
+}
+
+// pull 1: one thread per cell walks its (ordered) entries and updates d_dX once.
+template<typename Pt>
+__global__ void __launch_bounds__(128) pull_on_cells(int n_cells_max,
     const Pt* __restrict__ d_X, const Link* __restrict__ d_link,
     const int* __restrict__ offset, const int* __restrict__ entry,
     float strength, Pt* d_dX)
 {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells_max;
          c += gridDim.x * blockDim.x) {
         const int start = __ldg(offset + c), end = __ldg(offset + c + 1);
-        if (end <= start) continue;
+        if (end <= start || end - start > LINK_HUB) continue;
         float* out = reinterpret_cast<float*>(d_dX + c);
         float fx = out[0], fy = out[1], fz = out[2];
-        int last = -1;
-        for (int done = start; done < end; done++) {
-            int next = 0x7fffffff;
-            for (int q = start; q < end; q++) {
-                const int e = __ldg(entry + q);
-                if (e > last && e < next) next = e;
-            }
-            last = next;
-            const Link l = d_link[next >> 1];
-            const Pt r = load_pt(d_X, l.a) - load_pt(d_X, l.b);
-            const float dist = norm3df(r.x, r.y, r.z);
-            if (next & 1) {  // this cell is the b end
-                fx += strength * r.x / dist;
-                fy += strength * r.y / dist;
-                fz += strength * r.z / dist;
-            } else {
-                fx += -strength * r.x / dist;
-                fy += -strength * r.y / dist;
-                fz += -strength * r.z / dist;
-            }
-        }
+        for (int q = start; q < end; q++)
+            add_link_pull(d_X, d_link, __ldg(entry + q), strength, fx, fy, fz);
         out[0] = fx, out[1] = fy, out[2] = fz;
     }
+}
+
+// pull 2: one CTA per hub; thread t adds the entries t, t + 256, ... in that
+// order and the partial sums are combined by a fixed tree.
+template<typename Pt>
+__global__ void __launch_bounds__(LINK_HUB_THREADS) pull_on_hubs(
+    const Pt* __restrict__ d_X, const Link* __restrict__ d_link,
+    const int* __restrict__ offset, const int* __restrict__ entry,
+    const int* __restrict__ hubs, const int* __restrict__ hub_ctl,
+    float strength, Pt* d_dX)
+{
+    __shared__ float s_f[3][LINK_HUB_THREADS];
+    const int n_hubs = hub_ctl[0];
+    for (int h = blockIdx.x; h < n_hubs; h += gridDim.x) {
+        const int c = hubs[h];
+        const int start = offset[c], end = offset[c + 1];
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        for (int q = start + threadIdx.x; q < end; q += blockDim.x)
+            add_link_pull(d_X, d_link, entry[q], strength, fx, fy, fz);
+        s_f[0][threadIdx.x] = fx;
+        s_f[1][threadIdx.x] = fy;
+        s_f[2][threadIdx.x] = fz;
+        __syncthreads();
+        for (int d = LINK_HUB_THREADS / 2; d > 0; d >>= 1) {
+            if (threadIdx.x < d) {
+                s_f[0][threadIdx.x] += s_f[0][threadIdx.x + d];
+                s_f[1][threadIdx.x] += s_f[1][threadIdx.x + d];
+                s_f[2][threadIdx.x] += s_f[2][threadIdx.x + d];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            float* out = reinterpret_cast<float*>(d_dX + c);
+            out[0] += s_f[0][0], out[1] += s_f[1][0], out[2] += s_f[2][0];
+        }
+        __syncthreads();
+    }
+}
+
+// (Re)build the per-cell index of the link ends on stream s.
+inline void index_link_ends(Links& links, Link_segments& seg, int n_cells_max,
+    cudaStream_t s)
+{
+    const int sms = sm_count();
+    const int link_blocks = stride_grid(links.n_max, 256, sms);
+    const int n_tiles = ceil_div(n_cells_max + 1, SCAN_TILE);
+    bin_link_ends<<<link_blocks, 256, 0, s>>>(links.d_link, links.d_n,
+        links.n_max, n_cells_max, seg.count, seg.arrival, seg.hub_ctl);
+    scan_bins<<<n_tiles, SCAN_THREADS, 0, s>>>(
+        seg.count, seg.offset, n_tiles, seg.status, seg.ctl);
+    place_link_ends<<<link_blocks, 256, 0, s>>>(links.d_link, links.d_n,
+        links.n_max, seg.offset, seg.arrival, seg.entry);
+    order_link_ends<<<stride_grid(n_cells_max, 256, sms), 256, 0, s>>>(
+        n_cells_max, seg.offset, seg.entry, seg.hubs, seg.hub_ctl);
+    order_hub_segments<<<32, LINK_HUB_THREADS, 0, s>>>(
+        seg.offset, seg.entry, seg.arrival, seg.hubs, seg.hub_ctl);
+    YB_CUDA(cudaGetLastError());
 }
 
 template<typename Pt>
 void segmented_link_forces(Links& links, const Stage_context& stage,
     const Pt* d_X, Pt* d_dX)
 {
-    links.reserve_segments(stage.n_max_cells);
-    auto& seg = links.segments;
+    std::shared_ptr<Link_segments> seg = links.segments;
+    const int n_cells_max = stage.n_max_cells;
+    seg->reserve(n_cells_max, links.n_max);
     const cudaStream_t s = stage.stream;
+
+    // Is the index of the last build still good?
+    //  * cached topology: until the links are marked as changed;
+    //  * otherwise: within one solver step (stage 1 reuses stage 0's index).
+    // When a solver records its own step graph (hooks != nullptr) a cached
+    // index is kept up to date OUTSIDE the graph, by the replay hook; inside a
+    // caller's capture there is nobody to do that, so the per-step rule holds.
+    const bool cached = links.cache_topology &&
+                        !(stage.capturing && stage.hooks == nullptr);
+    const bool same_step = stage.stage == 1 && seg->built_by == stage.solver &&
+                           seg->built_in_step == stage.step_serial;
+    if (cached) {
+        if (seg->dirty) {
+            index_link_ends(links, *seg, n_cells_max,
+                stage.capturing ? stage.eager_stream : s);
+            seg->dirty = false;
+        }
+    } else if (!same_step || stage.solver == nullptr) {
+        index_link_ends(links, *seg, n_cells_max, s);
+        seg->dirty = true;  // good for this step only
+    }
+    seg->built_by = stage.solver;
+    seg->built_in_step = stage.step_serial;
+
     const int sms = sm_count();
-    const int link_blocks = stride_grid(links.n_max, 256, sms);
-    const int n_tiles = ceil_div(stage.n_cells + 1, SCAN_TILE);
-    bin_link_ends<<<link_blocks, 256, 0, s>>>(links.d_link, links.d_n,
-        links.n_max, stage.n_cells, seg.count, seg.arrival);
-    scan_bins<<<n_tiles, SCAN_THREADS, 0, s>>>(
-        seg.count, seg.offset, n_tiles, seg.status, seg.ctl);
-    place_link_ends<<<link_blocks, 256, 0, s>>>(links.d_link, links.d_n,
-        links.n_max, seg.offset, seg.arrival, seg.entry);
-    pull_on_cells<Pt><<<stride_grid(stage.n_cells, 128, sms), 128, 0, s>>>(
-        stage.n_cells, d_X, links.d_link, seg.offset, seg.entry,
+    pull_on_cells<Pt><<<stride_grid(n_cells_max, 128, sms), 128, 0, s>>>(
+        n_cells_max, d_X, links.d_link, seg->offset, seg->entry,
         links.strength, d_dX);
+    pull_on_hubs<Pt><<<32, LINK_HUB_THREADS, 0, s>>>(d_X, links.d_link,
+        seg->offset, seg->entry, seg->hubs, seg->hub_ctl, links.strength, d_dX);
     YB_CUDA(cudaGetLastError());
+
+    if (stage.capturing && stage.hooks != nullptr && stage.stage == 0) {
+        // What the recorded launches depend on: the Links object, its
+        // strength, and the caching mode. A cached index is refreshed here,
+        // on the stream the graph is about to be launched on.
+        Links* owner = &links;
+        const float strength = links.strength;
+        const bool was_cached = cached;
+        stage.hooks->push_back(
+            [seg, owner, strength, was_cached, n_cells_max](cudaStream_t launch) {
+                if (!seg->owner_alive) return false;
+                if (owner->strength != strength ||
+                    owner->cache_topology != was_cached)
+                    return false;
+                if (was_cached && seg->dirty) {
+                    index_link_ends(*owner, *seg, n_cells_max, launch);
+                    seg->dirty = false;
+                }
+                return true;
+            });
+    }
 }
 
 }  // namespace yb
@@ -326,7 +564,7 @@ template<typename Pt, Link_force<Pt> force>
 void link_forces(Links& links, const Pt* __restrict__ d_X, Pt* d_dX)
 {
     const yb::Stage_context* stage = yb::current_stage();
-    if (force == &linear_force<Pt> && stage != nullptr && stage->n_cells > 0) {
+    if (force == &linear_force<Pt> && stage != nullptr && stage->n_max_cells > 0) {
         yb::segmented_link_forces(links, *stage, d_X, d_dX);
         return;
     }

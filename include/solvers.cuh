@@ -125,14 +125,42 @@ inline bool graphs_enabled()
     return enabled;
 }
 
+// What a solver bakes into the kernel arguments of a captured step besides the
+// time step and the drift mode (compared field by field).
+struct Graph_key {
+    float a = 0.f, b = 0.f;
+    int c = 0, d = 0;
+    bool operator==(const Graph_key& o) const
+    {
+        return a == o.a && b == o.b && c == o.c && d == o.d;
+    }
+};
+
 // A captured Heun step. Kernel arguments are baked into the graph, so it is
-// keyed by everything the host passes by value.
+// keyed by everything the host passes by value; `hooks` are the checks that
+// capturable generic forces asked to run before every replay.
 struct Step_graph {
     const void* instantiation;  // identifies take_step<pw_int, pw_friction>
-    float dt, cube_size;
+    const void* forces_type;    // typeid of the generic forces, or nullptr
+    float dt;
+    Graph_key solver_key;
     int mode0, mode1, fix_point;
     cudaGraphExec_t exec;
+    std::vector<Replay_hook> hooks;
 };
+
+// Zero the derivative of the live cells before the generic forces add to it
+// (the count is read on the device: usable inside a captured step).
+template<typename Pt>
+__global__ void __launch_bounds__(256) zero_cells(
+    const int* __restrict__ d_n, int n_max, Pt* d_dX)
+{
+    const int n_floats = live_cells(d_n, n_max) * Layout<Pt>::lanes;
+    float* out = reinterpret_cast<float*>(d_dX);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_floats;
+         q += gridDim.x * blockDim.x)
+        out[q] = 0.f;
+}
 
 }  // namespace yb
 
@@ -176,19 +204,27 @@ public:
         free(h_n);
     }
 
-    // Both copies move all n_max elements plus n and block, as in the reference.
+    // Both copies move all n_max elements plus n and block, as in the
+    // reference. They are issued to the solver's stream and waited for, so
+    // they are ordered with the steps in flight whatever stream that is.
     void copy_to_device()
     {
         assert(*h_n <= n_max);
-        YB_CUDA(cudaMemcpy(d_X, h_X, static_cast<size_t>(n_max) * sizeof(Pt),
-            cudaMemcpyHostToDevice));
-        YB_CUDA(cudaMemcpy(d_n, h_n, sizeof(int), cudaMemcpyHostToDevice));
+        const cudaStream_t s = Solver<Pt>::stream;
+        YB_CUDA(cudaMemcpyAsync(d_X, h_X, static_cast<size_t>(n_max) * sizeof(Pt),
+            cudaMemcpyHostToDevice, s));
+        YB_CUDA(cudaMemcpyAsync(
+            d_n, h_n, sizeof(int), cudaMemcpyHostToDevice, s));
+        YB_CUDA(cudaStreamSynchronize(s));
     }
     void copy_to_host()
     {
-        YB_CUDA(cudaMemcpy(h_X, d_X, static_cast<size_t>(n_max) * sizeof(Pt),
-            cudaMemcpyDeviceToHost));
-        YB_CUDA(cudaMemcpy(h_n, d_n, sizeof(int), cudaMemcpyDeviceToHost));
+        const cudaStream_t s = Solver<Pt>::stream;
+        YB_CUDA(cudaMemcpyAsync(h_X, d_X, static_cast<size_t>(n_max) * sizeof(Pt),
+            cudaMemcpyDeviceToHost, s));
+        YB_CUDA(cudaMemcpyAsync(
+            h_n, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+        YB_CUDA(cudaStreamSynchronize(s));
         assert(*h_n <= n_max);
     }
     int get_d_n() { return Solver<Pt>::get_d_n(); }
@@ -366,7 +402,7 @@ public:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0)
             yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
-                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
         else
             yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
@@ -444,7 +480,7 @@ public:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0)
             yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
-                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
         else
             yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
@@ -519,63 +555,109 @@ protected:
                 ? (fix_com_z ? yb::DRIFT_POINT_XY_MEAN_Z : yb::DRIFT_MEAN)
                 : yb::DRIFT_POINT;
         const int mode1 = fix_com ? yb::DRIFT_MEAN : yb::DRIFT_POINT;
+        const bool seeded = !yb::is_no_gen_forces(gen_forces);
+        ++step_serial;
 
-        if (!yb::is_no_gen_forces(gen_forces)) {
-            // The callback is arbitrary host code that needs n: one read of
-            // d_n per step, then the stage kernels are issued directly. The
-            // read goes through a side stream while the grid build of the first stage
-            // (which needs neither n on the host nor the callback's output)
-            // already runs, so the device does not idle during the round trip.
-            YB_CUDA(cudaEventRecord(count_ready, stream));
-            YB_CUDA(cudaStreamWaitEvent(capture_stream, count_ready, 0));
-            YB_CUDA(cudaMemcpyAsync(h_n_pinned, d_n, sizeof(int),
-                cudaMemcpyDeviceToHost, capture_stream));
-            Computer<Pt>::index_ahead(stream, d_n, d_X, d_old_v, d_ctl);
-            YB_CUDA(cudaStreamSynchronize(capture_stream));
-            const int n = *h_n_pinned;
-            assert(n <= n_max);
-            enqueue_stage<pw_int, pw_friction, true>(
-                stream, 0, dt, mode0, n, gen_forces);
-            enqueue_stage<pw_int, pw_friction, true>(
-                stream, 1, dt, mode1, n, gen_forces);
+        // occupancy queries and attribute changes must not happen mid-capture
+        if (seeded)
+            Computer<Pt>::template prepare<pw_int, pw_friction, true>();
+        else
+            Computer<Pt>::template prepare<pw_int, pw_friction, false>();
+
+        // The caller is recording its own graph on the solver's stream (e.g. a
+        // whole model iteration): the stages join it. Generic forces must then
+        // be capturable, see capture_generic_forces.
+        cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &capture) != cudaSuccess) {
+            cudaGetLastError();
+            capture = cudaStreamCaptureStatusNone;
+        }
+        if (capture == cudaStreamCaptureStatusActive) {
+            enqueue_step<pw_int, pw_friction>(stream, dt, mode0, mode1, seeded,
+                n_max, gen_forces, true, nullptr);
             return;
         }
 
-        Generic_forces<Pt> none;
-        if (!yb::graphs_enabled() || profiling) {
-            enqueue_stage<pw_int, pw_friction, false>(
-                stream, 0, dt, mode0, 0, none);
-            enqueue_stage<pw_int, pw_friction, false>(
-                stream, 1, dt, mode1, 0, none);
+        const bool replayable = yb::graphs_enabled() && !profiling &&
+                                (!seeded || capture_generic_forces);
+        if (!replayable) {
+            int n = 0;
+            if (seeded) {
+                // The callback is arbitrary host code that needs n: one read
+                // of d_n per step, then the stage kernels are issued directly.
+                // The read goes through a side stream while the grid build of
+                // the first stage (which needs neither n on the host nor the
+                // callback's output) already runs, so the device does not idle
+                // during the round trip.
+                YB_CUDA(cudaEventRecord(count_ready, stream));
+                YB_CUDA(cudaStreamWaitEvent(capture_stream, count_ready, 0));
+                YB_CUDA(cudaMemcpyAsync(h_n_pinned, d_n, sizeof(int),
+                    cudaMemcpyDeviceToHost, capture_stream));
+                Computer<Pt>::index_ahead(stream, d_n, d_X, d_old_v, d_ctl);
+                YB_CUDA(cudaStreamSynchronize(capture_stream));
+                n = *h_n_pinned;
+                assert(n <= n_max);
+            }
+            enqueue_step<pw_int, pw_friction>(stream, dt, mode0, mode1, seeded,
+                n, gen_forces, false, nullptr);
             return;
         }
 
         static const char instantiation_tag = 0;
-        const float cube_size = Computer<Pt>::graph_key();
-        // occupancy queries and attribute changes must not happen mid-capture
-        Computer<Pt>::template prepare<pw_int, pw_friction, false>();
-        for (auto& g : graphs) {
-            if (g.instantiation == &instantiation_tag && g.dt == dt &&
-                g.cube_size == cube_size && g.mode0 == mode0 &&
-                g.mode1 == mode1 && g.fix_point == fix_point) {
+        const void* forces_type = seeded ? &gen_forces.target_type() : nullptr;
+        const yb::Graph_key solver_key = Computer<Pt>::graph_key();
+        for (size_t k = 0; k < graphs.size(); k++) {
+            auto& g = graphs[k];
+            if (g.instantiation != &instantiation_tag ||
+                g.forces_type != forces_type || g.dt != dt ||
+                !(g.solver_key == solver_key) || g.mode0 != mode0 ||
+                g.mode1 != mode1 || g.fix_point != fix_point)
+                continue;
+            bool valid = true;
+            for (auto& hook : g.hooks) valid = hook(stream) && valid;
+            if (valid) {
                 YB_CUDA(cudaGraphLaunch(g.exec, stream));
                 return;
             }
+            cudaGraphExecDestroy(g.exec);  // a force asked for a new capture
+            graphs.erase(graphs.begin() + k);
+            break;
         }
+        yb::Step_graph entry{&instantiation_tag, forces_type, dt, solver_key,
+            mode0, mode1, fix_point, nullptr, {}};
         cudaGraph_t graph;
+        // Relaxed: capturable forces may allocate scratch while being recorded.
         YB_CUDA(cudaStreamBeginCapture(
-            capture_stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_stage<pw_int, pw_friction, false>(
-            capture_stream, 0, dt, mode0, 0, none);
-        enqueue_stage<pw_int, pw_friction, false>(
-            capture_stream, 1, dt, mode1, 0, none);
+            capture_stream, cudaStreamCaptureModeRelaxed));
+        enqueue_step<pw_int, pw_friction>(capture_stream, dt, mode0, mode1,
+            seeded, n_max, gen_forces, true, &entry.hooks);
         YB_CUDA(cudaStreamEndCapture(capture_stream, &graph));
-        yb::Step_graph entry{&instantiation_tag, dt, cube_size, mode0, mode1,
-            fix_point, nullptr};
         YB_CUDA(cudaGraphInstantiate(&entry.exec, graph, 0));
         YB_CUDA(cudaGraphDestroy(graph));
-        graphs.push_back(entry);
         YB_CUDA(cudaGraphLaunch(entry.exec, stream));
+        graphs.push_back(std::move(entry));
+    }
+
+public:
+    // Extension: replay steps WITH generic forces from a captured CUDA graph
+    // too. Set it if the callable passed to take_step is "capturable": it
+    // only enqueues work on the step's stream (yb::current_stage()->stream,
+    // i.e. this solver's `stream` or the one recording it), enqueues the same
+    // work every call, and reads the live cell count from d_n on the device --
+    // the n it is handed is then n_max, an upper bound. link_forces,
+    // wall_forces and plain kernel launches / cudaMemsetAsync on that stream
+    // qualify; thrust calls and anything that reads device memory back do not.
+    // Graphs are keyed by the callable's type (one lambda expression = one
+    // graph), not by the values it captured.
+    bool capture_generic_forces = false;
+
+    // Drop every captured step (e.g. after changing something a capturable
+    // generic force baked into its launches).
+    void reset_graphs()
+    {
+        YB_CUDA(cudaStreamSynchronize(stream));
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
     }
 
 private:
@@ -588,22 +670,53 @@ private:
     cudaEvent_t count_ready = nullptr;
     yb::Slab_scratch slab;
     bool profiling = false;
+    unsigned long long step_serial = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
+    void enqueue_step(cudaStream_t s, float dt, int mode0, int mode1,
+        bool seeded, int n, Generic_forces<Pt>& gen_forces, bool capturing,
+        std::vector<yb::Replay_hook>* hooks)
+    {
+        if (seeded) {
+            enqueue_stage<pw_int, pw_friction, true>(
+                s, 0, dt, mode0, n, gen_forces, capturing, hooks);
+            enqueue_stage<pw_int, pw_friction, true>(
+                s, 1, dt, mode1, n, gen_forces, capturing, hooks);
+        } else {
+            enqueue_stage<pw_int, pw_friction, false>(
+                s, 0, dt, mode0, n, gen_forces, capturing, hooks);
+            enqueue_stage<pw_int, pw_friction, false>(
+                s, 1, dt, mode1, n, gen_forces, capturing, hooks);
+        }
+    }
 
     // One Heun stage: [seed dX with generic forces] -> pairwise sweep (writes
     // dX or dX1 and the stage's drift) -> predictor or corrector update.
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
         bool SEEDED>
     void enqueue_stage(cudaStream_t s, int stage, float dt, int drift_mode,
-        int n, Generic_forces<Pt>& gen_forces)
+        int n, Generic_forces<Pt>& gen_forces, bool capturing,
+        std::vector<yb::Replay_hook>* hooks)
     {
         const Pt* X_stage = stage == 0 ? d_X : d_X1;
         Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (SEEDED) {
-            YB_CUDA(cudaMemsetAsync(
-                dX_stage, 0, static_cast<size_t>(n) * sizeof(Pt), s));
+            if (capturing)
+                yb::zero_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, dX_stage);
+            else
+                YB_CUDA(cudaMemsetAsync(
+                    dX_stage, 0, static_cast<size_t>(n) * sizeof(Pt), s));
             // lets link_forces & co. see the cell count and the stream
             yb::Stage_context context{n, n_max, s};
+            context.d_n_cells = d_n;
+            context.stage = stage;
+            context.capturing = capturing;
+            context.solver = this;
+            context.step_serial = step_serial;
+            context.eager_stream = stream;
+            context.hooks = hooks;
             yb::current_stage() = &context;
             gen_forces(n, X_stage, dX_stage);
             yb::current_stage() = nullptr;
@@ -621,7 +734,6 @@ private:
             YB_CUDA(cudaEventRecord(sweep_stop, s));
             sweep_events.emplace_back(sweep_start, sweep_stop);
         }
-        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0) {
             Computer<Pt>::predict(s, blocks, d_n, dt, d_X, d_dX, d_X1, d_ctl);
         } else {
@@ -650,7 +762,10 @@ public:
     bool split_pairs = false;
 
 protected:
-    float graph_key() const { return split_pairs ? 1.f : 0.f; }
+    yb::Graph_key graph_key() const
+    {
+        return yb::Graph_key{0.f, 0.f, split_pairs ? 1 : 0, 0};
+    }
 
     const float4* dd_cube_order() const { return nullptr; }
 
@@ -707,7 +822,7 @@ protected:
         const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
     {
         yb::predictor_step<Pt, false><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
-            d_dX, d_X1, d_ctl, 1.f, 1, 1, nullptr, nullptr, nullptr);
+            d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
     }
 
 private:
@@ -786,6 +901,9 @@ public:
     int *d_cube_id, *d_point_id, *d_cube_start, *d_cube_end;
     Grid* d_grid;
     const int n_max, grid_size, n_cubes;
+    // Extension: the stream build() works on (default: the legacy stream, like
+    // the reference). Not part of the device copy's layout contract.
+    cudaStream_t stream = 0;
 
     Grid(int n_max, int gs = 50)
         : n_max{n_max}, grid_size{gs}, n_cubes{gs * gs * gs}
@@ -825,7 +943,7 @@ public:
         const int n, const Pt* __restrict__ d_X, const float cube_size = 1)
     {
         assert(n <= n_max);
-        const cudaStream_t s = 0;
+        const cudaStream_t s = stream;
         const int sms = yb::sm_count();
         YB_CUDA(cudaMemcpyAsync(
             d_n_scratch, &n, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -879,13 +997,23 @@ public:
         YB_CUDA(cudaMalloc(
             &aux, cells * yb::Layout<Pt>::aux_vec4 * sizeof(float4)));
         YB_CUDA(cudaMalloc(&cube_sorted, cells * sizeof(int)));
-        YB_CUDA(cudaMalloc(&staged,
-            cells * (1 + yb::Layout<Pt>::aux_vec4) * sizeof(float4)));
+        if (split_sweep()) {
+            nb_stride = (n_max > 0 ? n_max : 1) + 31 & ~31;
+            YB_CUDA(cudaMalloc(
+                &nb, size_t(nb_stride) * yb::LIST_MAX * sizeof(int)));
+            YB_CUDA(cudaMalloc(&nb_count, size_t(nb_stride) * sizeof(int)));
+        }
+        // scratch of the state-carrying build tail only
+        if (carry_state())
+            YB_CUDA(cudaMalloc(&staged,
+                cells * (1 + yb::Layout<Pt>::aux_vec4) * sizeof(float4)));
     }
     Grid_computer(const Grid_computer&) = delete;
     Grid_computer& operator=(const Grid_computer&) = delete;
     ~Grid_computer()
     {
+        cudaFree(nb_count);
+        cudaFree(nb);
         cudaFree(staged);
         cudaFree(cube_sorted);
         cudaFree(aux);
@@ -894,7 +1022,11 @@ public:
     }
 
 protected:
-    float graph_key() const { return cube_size; }
+    // everything the stage kernels get by value
+    yb::Graph_key graph_key() const
+    {
+        return yb::Graph_key{cube_size, 0.f, z_half, active_cubes};
+    }
 
     // Resident CTAs per SM of a persistent sweep kernel (queried once).
     template<typename Kernel>
@@ -933,7 +1065,46 @@ protected:
         static const int ctas_per_sm =
             resident_ctas(yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>,
                 yb::SWEEP_THREADS, yb::Sweep_config<yb::Layout<Pt>::lanes>::smem);
+        if (split_sweep()) {
+            prepare_list();
+            prepare_interact<pw_int, pw_friction, SEEDED>();
+        }
         return ctas_per_sm;
+    }
+    static int prepare_list()
+    {
+        static const int ctas_per_sm = resident_ctas(
+            yb::list_cubes, yb::SWEEP_THREADS, yb::List_config::smem);
+        return ctas_per_sm;
+    }
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    static int prepare_interact()
+    {
+        // no shared memory to speak of: all of the SM's array is L1
+        static const int ctas_per_sm = [] {
+            auto kernel = yb::interact_lists<Pt, pw_int, pw_friction, SEEDED>;
+            YB_CUDA(cudaFuncSetAttribute(kernel,
+                cudaFuncAttributePreferredSharedMemoryCarveout,
+                cudaSharedmemCarveoutMaxL1));
+            int resident = 0;
+            YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &resident, kernel, yb::SWEEP_THREADS, 0));
+            return resident < 1 ? 1 : resident;
+        }();
+        return ctas_per_sm;
+    }
+
+    // Points with extra lanes run the sweep as two kernels (b200/pair_sweep.cuh,
+    // list_cubes + interact_lists); YALLA_B200_SPLIT_SWEEP=0/1 overrides.
+    static bool split_sweep()
+    {
+        static const int forced = [] {
+            const char* env = getenv("YALLA_B200_SPLIT_SWEEP");
+            return env && env[0] ? atoi(env) : -1;
+        }();
+        if (forced >= 0) return forced != 0;
+        return yb::Layout<Pt>::lanes > 4;
     }
 
     // Cube ids -> bucket sort -> state in cube order (b200/grid_build.cuh).
@@ -1019,27 +1190,46 @@ protected:
         const int ctas = persistent_ctas(
             prepare<pw_int, pw_friction, SEEDED>(), yb::SWEEP_THREADS, max_ctas);
         if (before_sweep) YB_CUDA(cudaEventRecord(before_sweep, s));
+        const bool split = split_sweep();
+        if (split) {
+            yb::list_cubes<<<persistent_ctas(prepare_list(), yb::SWEEP_THREADS,
+                                 max_ctas),
+                yb::SWEEP_THREADS, yb::List_config::smem, s>>>(d_n, n_max, pos4,
+                cube_sorted, sort.offset, cube_size, grid_size, z_half,
+                active_cubes, nb, nb_count, nb_stride, d_ctl);
+            yb::interact_lists<Pt, pw_int, pw_friction, SEEDED>
+                <<<persistent_ctas(
+                       prepare_interact<pw_int, pw_friction, SEEDED>(),
+                       yb::SWEEP_THREADS, max_ctas),
+                    yb::SWEEP_THREADS, 0, s>>>(d_n, n_max, pos4, aux, nb,
+                    nb_count, nb_stride, cube_size, d_dX, d_partials, stage,
+                    drift_mode, fix_point, d_ctl);
+        }
+        // alone, or as the fallback for crowded tissues behind the pair above
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::SWEEP_THREADS,
                 yb::Sweep_config<yb::Layout<Pt>::lanes>::smem, s>>>(d_n, n_max, pos4,
                 aux, cube_sorted, sort.offset, cube_size, grid_size, z_half,
                 active_cubes, d_dX, d_partials, stage, drift_mode, fix_point,
-                d_ctl);
+                d_ctl, split ? 1 : 0);
     }
 
     void predict(cudaStream_t s, int blocks, const int* d_n, float dt,
         const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
     {
         yb::predictor_step<Pt, true><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
-            d_dX, d_X1, d_ctl, cube_size, grid_size, n_cubes, sort.key,
-            sort.arrival, sort.count);
+            d_dX, d_X1, d_ctl, cube_size, grid_size, z_half, active_cubes,
+            sort.key, sort.arrival, sort.count);
     }
 
     yb::Bucket_sort sort;
     float4* pos4;
     float4* aux;
     int* cube_sorted;
-    float4* staged;  // cube order, arrival order inside cubes (place_cells)
+    float4* staged = nullptr;  // cube order, arrival order inside cubes (place_cells)
+    int* nb = nullptr;         // neighbour lists of the split sweep, entry-major
+    int* nb_count = nullptr;
+    int nb_stride = 0;
     const int n_max, grid_size, n_cubes;
     // z numbering of the grid: the reference's cubic grid by default; a slab of
     // a decomposed domain uses only its own layers (dd_slab_grid below)

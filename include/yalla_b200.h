@@ -86,6 +86,10 @@ int yb_sim_set_param(yb_sim* sim, const char* name, double value);
 int yb_sim_set_state(yb_sim* sim, const float* h_X, int n, int reset_v);
 int yb_sim_get_state(yb_sim* sim, float* h_X, int capacity, int* n_out);
 int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity);
+/* Replace the old velocities (d_old_v, 3 floats per cell) of the first n cells;
+ * with yb_sim_set_state(..., reset_v = 0) this restarts a model from a state
+ * another library produced (the step-by-step parity tests do). Blocks. */
+int yb_sim_set_velocities(yb_sim* sim, const float* h_v, int n);
 
 /* Integer per-cell properties of the model by name ("type", "mes_nbs",
  * "epi_nbs", ...): Property<int>::copy_to_device / copy_to_host. */
@@ -118,15 +122,27 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
 int yb_sim_step_host(yb_sim* sim, const float* h_in, int n, float dt,
     int n_steps, float* h_out, int capacity, int* n_out);
 
-/* Extensions for pipelining independent batches (product library only): give
- * a model its own CUDA stream (a cudaStream_t; default: the legacy default
- * stream like every ya||a launch), and a host-buffer step that only ENQUEUES
- * the upload of n cells, n_steps steps and the download of out_cells cells to
- * h_out plus the final cell count to *h_n_out (both pinned). The caller waits
- * on the stream before reading them. */
+/* Extensions for pipelining independent batches (product library only).
+ * yb_sim_set_stream gives a model its own CUDA stream (a cudaStream_t;
+ * default: the legacy default stream like every ya||a launch); it waits for
+ * the work already issued to the old one.
+ * yb_sim_step_host_async only ENQUEUES: the upload of n cells from h_in
+ * (pinned) on a copy stream, n_steps steps on the model's stream, and the
+ * download of out_cells cells to h_out plus the final cell count to *h_n_out
+ * (both pinned) on a second copy stream, through two staging slots in device
+ * memory -- so the copies of consecutive calls overlap the steps of the batch
+ * in between, with ONE model instance. At most two batches are in flight; the
+ * third call waits for the first one's buffers. yb_sim_host_drain waits until
+ * everything enqueued so far has landed in the host buffers.
+ *
+ * The "growth" and "branching" models reach their Property arrays through
+ * process-global __device__ pointers (as the reference examples do), so only
+ * one instance of them is active at a time: a step of another instance first
+ * waits for the stream of the one that ran before. */
 int yb_sim_set_stream(yb_sim* sim, void* stream);
 int yb_sim_step_host_async(yb_sim* sim, const float* h_in, int n, float dt,
     int n_steps, float* h_out, int out_cells, int* h_n_out);
+int yb_sim_host_drain(yb_sim* sim);
 
 /* Time the dominant kernel (the pairwise sweep) with CUDA events on the
  * launching stream: enable, run steps, then read the accumulated milliseconds

@@ -397,6 +397,7 @@ struct yb_sim {
     virtual int set_state(const float*, int, int) = 0;
     virtual int get_state(float*, int, int*) = 0;
     virtual int get_velocities(float*, int) = 0;
+    virtual int set_velocities(const float*, int) = 0;
     virtual int set_ints(const std::string&, const int*, int) = 0;
     virtual int get_ints(const std::string&, int*, int) = 0;
     virtual int set_links(const int*, int) = 0;
@@ -496,6 +497,12 @@ struct Sim : yb_sim {
     {
         if (n > cap) return fail(YB_EINVAL, "capacity < n");
         memcpy(h_v, old_v.data(), sizeof(F3) * size_t(n));
+        return YB_OK;
+    }
+    int set_velocities(const float* h_v, int count) override
+    {
+        if (count < 0 || count > capacity) return fail(YB_EINVAL, "n > n_max");
+        memcpy(old_v.data(), h_v, sizeof(F3) * size_t(count));
         return YB_OK;
     }
     int set_ints(const std::string& name, const int* values, int count) override
@@ -926,6 +933,10 @@ int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity)
 {
     return sim->get_velocities(h_v, capacity);
 }
+int yb_sim_set_velocities(yb_sim* sim, const float* h_v, int n)
+{
+    return sim->set_velocities(h_v, n);
+}
 int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n)
 {
     return sim->set_ints(name, h_values, n);
@@ -1026,6 +1037,10 @@ int yb_sim_set_stream(yb_sim*, void*)
 }
 int yb_sim_step_host_async(
     yb_sim*, const float*, int, float, int, float*, int, int*)
+{
+    return fail(YB_ENOSYS, "asynchronous steps need the product library");
+}
+int yb_sim_host_drain(yb_sim*)
 {
     return fail(YB_ENOSYS, "asynchronous steps need the product library");
 }

@@ -22,6 +22,8 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_LIB = os.environ.get("YALLA_B200_LIB") or os.path.join(
     _ROOT, "yalla_b200", "_lib", "libyalla_b200.so")
 REFERENCE_LIB = os.path.join(_ROOT, "oracle", "_ref", "libyalla_ref.so")
+REFERENCE_NDEBUG_LIB = os.path.join(_ROOT, "oracle", "_ref",
+                                    "libyalla_ref_ndebug.so")
 
 YB_OK, YB_EINVAL, YB_ECUDA, YB_ENOSYS = 0, -1, -2, -3
 
@@ -46,6 +48,9 @@ SIGNATURES = {
                                         ctypes.c_int, _c_int_p]),
     "yb_sim_get_velocities": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_int]),
+    "yb_sim_set_velocities": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int]),
+    "yb_sim_host_drain": (ctypes.c_int, [ctypes.c_void_p]),
     "yb_sim_set_ints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
                                        ctypes.c_void_p, ctypes.c_int]),
     "yb_sim_get_ints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p,
@@ -246,6 +251,11 @@ class Sim:
             self.handle, out.ctypes.data, self.n_max), "get_velocities")
         return out[:self.n()].copy()
 
+    def set_velocities(self, v):
+        v = _f32(v).reshape(-1, 3)
+        self.lib.check(self.lib.cdll.yb_sim_set_velocities(
+            self.handle, v.ctypes.data, len(v)), "set_velocities")
+
     def set_ints(self, name, values):
         values = _i32(values)
         self.lib.check(self.lib.cdll.yb_sim_set_ints(
@@ -357,11 +367,16 @@ class Sim:
                        "set_stream")
 
     def step_host_async(self, X_in, dt, n_steps, X_out, out_cells, n_out_ptr):
-        """Enqueue upload, steps and download on the model's stream; X_in, X_out
-        and the int at n_out_ptr must be pinned host memory."""
+        """Enqueue upload, steps and download (copy streams + the model's
+        stream); X_in, X_out and the int at n_out_ptr must be pinned host memory;
+        host_drain() waits."""
         self.lib.check(self.lib.cdll.yb_sim_step_host_async(
             self.handle, X_in.ctypes.data, len(X_in), dt, n_steps,
             X_out.ctypes.data, out_cells, n_out_ptr), "step_host_async")
+
+    def host_drain(self):
+        """Wait for every batch enqueued with step_host_async."""
+        self.lib.check(self.lib.cdll.yb_sim_host_drain(self.handle), "host_drain")
 
     def n(self):
         n = ctypes.c_int()

@@ -55,6 +55,20 @@ def build_product(force=False):
     return out
 
 
+def build_variant(name, defines):
+    """A tuning variant of the product library (-D overrides of the kernel
+    budgets) -> yalla_b200/_lib/variants/<name>.so; picked up through the
+    YALLA_B200_LIB environment variable (scripts/tune_variants.sh)."""
+    out = os.path.join(ROOT, "yalla_b200", "_lib", "variants", name + ".so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    _run(["nvcc"] + NVCC_FLAGS + [f"-D{d}" for d in defines] +
+         ["-Xcompiler", "-fPIC", "-shared",
+          "-I", os.path.join(ROOT, "include"),
+          "-I", os.path.join(ROOT, "yalla_b200", "csrc"),
+          "-o", out, os.path.join(ROOT, "yalla_b200", "csrc", "capi.cu")])
+    return out
+
+
 def build_extension_tests(force=False):
     """tests/cuda/*.cu -- GPU test programs for header-level extensions that
     have no C-ABI entry -- into tests/_bin/ (run by tests/test_extensions_gpu.py)."""

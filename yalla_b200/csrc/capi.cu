@@ -49,6 +49,7 @@ struct yb_sim {
     virtual int set_state(const float* h_X, int n, int reset_v) = 0;
     virtual int get_state(float* h_X, int capacity, int* n_out) = 0;
     virtual int get_velocities(float* h_v, int capacity) = 0;
+    virtual int set_velocities(const float* h_v, int n) = 0;
     virtual int set_ints(const std::string& name, const int* values, int n)
     {
         return fail(YB_EINVAL, "model has no int property " + name);
@@ -86,6 +87,12 @@ struct yb_sim {
     {
         return fail(YB_ENOSYS, "asynchronous steps need the product library");
     }
+    virtual int host_drain()
+    {
+        return fail(YB_ENOSYS, "asynchronous steps need the product library");
+    }
+    // the stream the model's work is issued to
+    virtual cudaStream_t work_stream() { return 0; }
     // Device address of the current cell count (for asynchronous snapshots).
     virtual const int* count_on_device() = 0;
     virtual int current_n() = 0;
@@ -164,9 +171,11 @@ struct Sim_base : yb_sim {
         memcpy(cells.h_X, h_X, sizeof(Pt) * static_cast<size_t>(n));
         *cells.h_n = n;
         cells.copy_to_device();
-        if (reset_v)
-            cudaMemset(cells.d_old_v, 0,
-                sizeof(float3) * static_cast<size_t>(cells.n_max));
+        if (reset_v) {
+            cudaMemsetAsync(cells.d_old_v, 0,
+                sizeof(float3) * static_cast<size_t>(cells.n_max), model_stream());
+            cudaStreamSynchronize(model_stream());
+        }
         n_host = n;
         return check_cuda("set_state");
     }
@@ -184,10 +193,20 @@ struct Sim_base : yb_sim {
     {
         const int n = cells.get_d_n();
         if (n > capacity) return fail(YB_EINVAL, "capacity < n");
-        cudaMemcpy(h_v, cells.d_old_v, sizeof(float3) * static_cast<size_t>(n),
-            cudaMemcpyDeviceToHost);
+        cudaMemcpyAsync(h_v, cells.d_old_v, sizeof(float3) * static_cast<size_t>(n),
+            cudaMemcpyDeviceToHost, model_stream());
+        cudaStreamSynchronize(model_stream());
         return check_cuda("get_velocities");
     }
+    int set_velocities(const float* h_v, int n) override
+    {
+        if (n < 0 || n > cells.n_max) return fail(YB_EINVAL, "n > n_max");
+        cudaMemcpyAsync(cells.d_old_v, h_v, sizeof(float3) * static_cast<size_t>(n),
+            cudaMemcpyHostToDevice, model_stream());
+        cudaStreamSynchronize(model_stream());
+        return check_cuda("set_velocities");
+    }
+    cudaStream_t work_stream() override { return model_stream(); }
     int current_n() override { return n_host = cells.get_d_n(); }
     const int* count_on_device() override { return cells.d_n; }
     // stream the model's own kernels are launched on (the solver's stream)
@@ -202,23 +221,122 @@ struct Sim_base : yb_sim {
 #ifdef YALLA_B200
     int set_stream(void* stream) override
     {
+        cudaStreamSynchronize(cells.stream);
         cells.stream = static_cast<cudaStream_t>(stream);
+        stream_changed();
         return YB_OK;
     }
+    virtual void stream_changed() {}
+
+    // ---- pipelined host-buffer steps ---------------------------------------
+    // Independent batches through this one model instance: the upload of
+    // batch k + 1 and the download of batch k - 1 run on two copy streams
+    // while batch k integrates, through two staging slots in device memory.
+    // Events order slot reuse; nothing here waits on the host except when a
+    // slot's previous download has not been drained yet.
+    struct Host_pipeline {
+        cudaStream_t up = nullptr, down = nullptr;
+        Pt* d_in[2] = {nullptr, nullptr};
+        Pt* d_out[2] = {nullptr, nullptr};
+        int* d_counts = nullptr;  // [0..1] n per slot in, [2..3] n per slot out
+        int* h_n_in = nullptr;    // pinned, one per slot
+        cudaEvent_t uploaded[2], consumed[2], computed[2], downloaded[2];
+        bool used[2] = {false, false};
+        int next = 0;
+    } pipe;
+
+    void open_pipeline()
+    {
+        if (pipe.up) return;
+        const size_t bytes = sizeof(Pt) * static_cast<size_t>(cells.n_max);
+        cudaStreamCreateWithFlags(&pipe.up, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&pipe.down, cudaStreamNonBlocking);
+        for (int k = 0; k < 2; k++) {
+            cudaMalloc(&pipe.d_in[k], bytes);
+            cudaMalloc(&pipe.d_out[k], bytes);
+            cudaEventCreateWithFlags(&pipe.uploaded[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&pipe.consumed[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&pipe.computed[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&pipe.downloaded[k], cudaEventDisableTiming);
+        }
+        cudaMalloc(&pipe.d_counts, 4 * sizeof(int));
+        cudaMallocHost(&pipe.h_n_in, 2 * sizeof(int));
+    }
+    void close_pipeline()
+    {
+        if (!pipe.up) return;
+        cudaStreamSynchronize(pipe.up);
+        cudaStreamSynchronize(pipe.down);
+        for (int k = 0; k < 2; k++) {
+            cudaFree(pipe.d_in[k]);
+            cudaFree(pipe.d_out[k]);
+            cudaEventDestroy(pipe.uploaded[k]);
+            cudaEventDestroy(pipe.consumed[k]);
+            cudaEventDestroy(pipe.computed[k]);
+            cudaEventDestroy(pipe.downloaded[k]);
+        }
+        cudaFree(pipe.d_counts);
+        cudaFreeHost(pipe.h_n_in);
+        cudaStreamDestroy(pipe.up);
+        cudaStreamDestroy(pipe.down);
+        pipe.up = pipe.down = nullptr;
+    }
+    ~Sim_base() override { close_pipeline(); }
+
     // Enqueue upload, steps and the download of `out_cells` cells plus the
-    // count (into pinned *h_n_out); the caller waits on the stream.
+    // count (into pinned *h_n_out); yb_sim_host_drain waits for all of it.
     int step_host_async(const float* h_in, int n, float dt, int n_steps,
         float* h_out, int out_cells, int* h_n_out) override
     {
         if (n < 0 || n > cells.n_max || out_cells > cells.n_max)
             return fail(YB_EINVAL, "n > n_max");
-        cells.upload(reinterpret_cast<const Pt*>(h_in), n);
-        for (int k = 0; k < n_steps; k++) this->step(dt);
-        cudaMemcpyAsync(h_out, cells.d_X, sizeof(Pt) * size_t(out_cells),
-            cudaMemcpyDeviceToHost, cells.stream);
-        cudaMemcpyAsync(h_n_out, cells.d_n, sizeof(int), cudaMemcpyDeviceToHost,
-            cells.stream);
+        open_pipeline();
+        const int k = pipe.next;
+        pipe.next ^= 1;
+        const cudaStream_t work = cells.stream;
+        if (pipe.used[k]) {
+            // the slot's input was consumed and its output drained?
+            cudaStreamWaitEvent(pipe.up, pipe.consumed[k], 0);
+            cudaStreamWaitEvent(work, pipe.downloaded[k], 0);
+            cudaEventSynchronize(pipe.consumed[k]);  // h_n_in[k] is free again
+        }
+        pipe.h_n_in[k] = n;
+        cudaMemcpyAsync(pipe.d_in[k], h_in, sizeof(Pt) * size_t(n),
+            cudaMemcpyHostToDevice, pipe.up);
+        cudaMemcpyAsync(pipe.d_counts + k, pipe.h_n_in + k, sizeof(int),
+            cudaMemcpyHostToDevice, pipe.up);
+        cudaEventRecord(pipe.uploaded[k], pipe.up);
+
+        cudaStreamWaitEvent(work, pipe.uploaded[k], 0);
+        cudaMemcpyAsync(cells.d_X, pipe.d_in[k], sizeof(Pt) * size_t(n),
+            cudaMemcpyDeviceToDevice, work);
+        cudaMemcpyAsync(cells.d_n, pipe.d_counts + k, sizeof(int),
+            cudaMemcpyDeviceToDevice, work);
+        cudaEventRecord(pipe.consumed[k], work);
+        for (int q = 0; q < n_steps; q++) this->step(dt);
+        cudaMemcpyAsync(pipe.d_out[k], cells.d_X, sizeof(Pt) * size_t(out_cells),
+            cudaMemcpyDeviceToDevice, work);
+        cudaMemcpyAsync(pipe.d_counts + 2 + k, cells.d_n, sizeof(int),
+            cudaMemcpyDeviceToDevice, work);
+        cudaEventRecord(pipe.computed[k], work);
+
+        cudaStreamWaitEvent(pipe.down, pipe.computed[k], 0);
+        cudaMemcpyAsync(h_out, pipe.d_out[k], sizeof(Pt) * size_t(out_cells),
+            cudaMemcpyDeviceToHost, pipe.down);
+        cudaMemcpyAsync(h_n_out, pipe.d_counts + 2 + k, sizeof(int),
+            cudaMemcpyDeviceToHost, pipe.down);
+        cudaEventRecord(pipe.downloaded[k], pipe.down);
+        pipe.used[k] = true;
         return check_cuda("yb_sim_step_host_async");
+    }
+    int host_drain() override
+    {
+        if (pipe.up) {
+            cudaStreamSynchronize(pipe.up);
+            cudaStreamSynchronize(cells.stream);
+            cudaStreamSynchronize(pipe.down);
+        }
+        return check_cuda("yb_sim_host_drain");
     }
     // n live cells straight between the caller's buffers and the device
     // (Solution::copy_to_device/host move n_max cells through h_X)
@@ -234,9 +352,11 @@ struct Sim_base : yb_sim {
         if (n_out) *n_out = n_host;
         return check_cuda("yb_sim_step_host");
     }
+    bool profiling_sweeps = false;
     int profile_sweeps(int enable) override
     {
         cells.profile_sweeps(enable != 0);
+        profiling_sweeps = enable != 0;
         return YB_OK;
     }
     int read_sweep_profile(float* total_ms, int* launches) override
@@ -257,17 +377,19 @@ struct Sim_base : yb_sim {
         float3* v = cells.dd_velocities();
         const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
         if (stage == 0) {
-            cudaMemcpyAsync(X, X_owned, sizeof(Pt) * size_t(n_owned), d2d, 0);
-            cudaMemcpyAsync(v, v_owned, sizeof(float3) * size_t(n_owned), d2d, 0);
+            cudaMemcpyAsync(
+                X, X_owned, sizeof(Pt) * size_t(n_owned), d2d, cells.stream);
+            cudaMemcpyAsync(
+                v, v_owned, sizeof(float3) * size_t(n_owned), d2d, cells.stream);
             dd_n_owned = n_owned;
         } else if (n_owned != dd_n_owned) {
             return fail(YB_EINVAL, "stage 1 must keep the owned cells of stage 0");
         }
         if (n_ghost > 0) {
             cudaMemcpyAsync(X + n_owned, X_ghost, sizeof(Pt) * size_t(n_ghost),
-                d2d, 0);
+                d2d, cells.stream);
             cudaMemcpyAsync(v + n_owned, v_ghost,
-                sizeof(float3) * size_t(n_ghost), d2d, 0);
+                sizeof(float3) * size_t(n_ghost), d2d, cells.stream);
         }
         cells.dd_set_counts(n_owned, n_owned + n_ghost);
         return check_cuda("yb_dd_load");
@@ -283,10 +405,10 @@ struct Sim_base : yb_sim {
         const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
         if (which == 0 || which == 1)
             cudaMemcpyAsync(out, cells.dd_positions(which),
-                sizeof(Pt) * size_t(n), d2d, 0);
+                sizeof(Pt) * size_t(n), d2d, cells.stream);
         else
             cudaMemcpyAsync(out, cells.dd_velocities(),
-                sizeof(float3) * size_t(n), d2d, 0);
+                sizeof(float3) * size_t(n), d2d, cells.stream);
         return check_cuda("yb_dd_read");
     }
     int slab_begin(float z_lo, float z_hi, float halo, int capacity,
@@ -342,7 +464,7 @@ struct Sim_base : yb_sim {
     {
         cells.template dd_forces<force, friction>(stage);
         cudaMemcpyAsync(sums4, cells.dd_drift_sum(stage), 4 * sizeof(float),
-            cudaMemcpyDeviceToDevice, 0);
+            cudaMemcpyDeviceToDevice, cells.stream);
         return check_cuda("yb_dd_forces");
     }
 #endif
@@ -443,6 +565,13 @@ struct Protrusion_sim : Sim_base<float3, Grid_solver> {
         : Base{n_max, grid_size, cube_size}, links{4 * n_max}
     {
         links.set_d_n(0);
+#ifdef YALLA_B200
+        // link_forces only enqueues kernels on the step's stream: the whole
+        // step replays from one CUDA graph; the links only change through
+        // set_links (copy_to_device), so their per-cell index is kept.
+        cells.capture_generic_forces = true;
+        links.cache_topology = true;
+#endif
     }
     int set_param(const std::string& name, double value) override
     {
@@ -514,21 +643,52 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
         type.copy_to_device();
         n_mes_nbs.copy_to_device();
         n_epi_nbs.copy_to_device();
-        bind();
     }
-    // The functors find the property arrays through __device__ pointers.
+    // The functors find the property arrays through __device__ pointers
+    // (models.cuh), which are global to the process: one Typed_sim is bound
+    // at a time. Binding another one first waits for the stream of the model
+    // that was bound before, so the kernels of two such models never overlap
+    // with the wrong pointers in place; a model that stays bound pays nothing.
+    struct Binding {
+        const void* owner = nullptr;
+        cudaStream_t stream = 0;
+    };
+    static Binding& binding()
+    {
+        static Binding current;
+        return current;
+    }
     void bind()
     {
-        cudaMemcpyToSymbol(models::d_type, &type.d_prop, sizeof(type.d_prop));
-        cudaMemcpyToSymbol(
-            models::d_mes_nbs, &n_mes_nbs.d_prop, sizeof(n_mes_nbs.d_prop));
-        cudaMemcpyToSymbol(
-            models::d_epi_nbs, &n_epi_nbs.d_prop, sizeof(n_epi_nbs.d_prop));
+        Binding& current = binding();
+        if (current.owner == this) return;
+        if (current.owner != nullptr) cudaStreamSynchronize(current.stream);
+        const cudaStream_t s = this->model_stream();
+        cudaMemcpyToSymbolAsync(models::d_type, &type.d_prop, sizeof(type.d_prop),
+            0, cudaMemcpyHostToDevice, s);
+        cudaMemcpyToSymbolAsync(models::d_mes_nbs, &n_mes_nbs.d_prop,
+            sizeof(n_mes_nbs.d_prop), 0, cudaMemcpyHostToDevice, s);
+        cudaMemcpyToSymbolAsync(models::d_epi_nbs, &n_epi_nbs.d_prop,
+            sizeof(n_epi_nbs.d_prop), 0, cudaMemcpyHostToDevice, s);
+        current.owner = this;
+        current.stream = s;
     }
+    void unbind()
+    {
+        Binding& current = binding();
+        if (current.owner != this) return;
+        cudaStreamSynchronize(current.stream);
+        current.owner = nullptr;
+    }
+    ~Typed_sim() override { unbind(); }
+#ifdef YALLA_B200
+    void stream_changed() override { unbind(); }
+#endif
     int set_ints(const std::string& name, const int* values, int n) override
     {
         if (n > this->cells.n_max) return fail(YB_EINVAL, "n > n_max");
         if (name == "type") {
+            cudaStreamSynchronize(this->model_stream());
             for (int i = 0; i < n; i++)
                 type.h_prop[i] = static_cast<models::Cell_types>(values[i]);
             type.copy_to_device();
@@ -538,7 +698,7 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
     }
     int get_ints(const std::string& name, int* values, int capacity) override
     {
-        const int n = this->cells.get_d_n();
+        const int n = this->cells.get_d_n();  // waits for the model's stream
         if (n > capacity) return fail(YB_EINVAL, "capacity < n");
         if (name == "type") {
             type.copy_to_host();
@@ -558,10 +718,14 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
     // n handed to the callback instead of reading d_n back.
     void reset_counters(int n)
     {
-        cudaMemsetAsync(
-            n_mes_nbs.d_prop, 0, sizeof(int) * size_t(n), this->model_stream());
-        cudaMemsetAsync(
-            n_epi_nbs.d_prop, 0, sizeof(int) * size_t(n), this->model_stream());
+        // inside the generic-forces callback: the stream of the step, which is
+        // the solver's recording stream while a step is being captured
+        cudaStream_t s = this->model_stream();
+#ifdef YALLA_B200
+        if (const yb::Stage_context* stage = yb::current_stage()) s = stage->stream;
+#endif
+        cudaMemsetAsync(n_mes_nbs.d_prop, 0, sizeof(int) * size_t(n), s);
+        cudaMemsetAsync(n_epi_nbs.d_prop, 0, sizeof(int) * size_t(n), s);
     }
 };
 
@@ -585,11 +749,18 @@ struct Growth_sim : Typed_sim<Po_cell> {
     }
     ~Growth_sim() override
     {
+#ifdef YALLA_B200
+        drop_iteration();
+        if (recording_stream) cudaStreamDestroy(recording_stream);
+#endif
         cudaFree(d_n_at_launch);
         cudaFree(d_state);
     }
     int set_param(const std::string& name, double value) override
     {
+#ifdef YALLA_B200
+        drop_iteration();  // parameters are baked into the recorded launches
+#endif
         if (name == "prolif_rate") {
             prolif_rate = static_cast<float>(value);
         } else if (name == "mean_dist") {
@@ -609,29 +780,13 @@ struct Growth_sim : Typed_sim<Po_cell> {
         }
         return YB_OK;
     }
-    int step(float dt) override
+    // What examples/passive_growth.cu does per iteration on the device.
+    void enqueue_iteration(float dt)
     {
         const int n_max = cells.n_max;
-        if (!seeded) {
-            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, model_stream()>>>(
-                n_max, seed, d_state);
-            seeded = true;
-        }
-        bind();
         auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
                              Po_cell* d_dX) { reset_counters(n); };
         cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
-#ifdef YALLA_B200
-        if (prolif_rate > 0 && reproducible) {
-            if (!division)
-                division.reset(new Cell_division<Po_cell>(n_max, seed));
-            cudaMemcpyToSymbolAsync(models::d_prolif_rate, &prolif_rate,
-                sizeof(float), 0, cudaMemcpyHostToDevice, model_stream());
-            division->divide<models::growth_division_rate, models::growth_inherit>(
-                cells, mean_dist);
-            return 0;
-        }
-#endif
         if (prolif_rate > 0) {
             // sized for the capacity; the kernel reads the live count itself
             models::snapshot_count<<<1, 1, 0, model_stream()>>>(
@@ -641,15 +796,90 @@ struct Growth_sim : Typed_sim<Po_cell> {
                 mean_dist, n_max, d_state, cells.d_X, cells.d_old_v, cells.d_n,
                 d_n_at_launch);
         }
+    }
+
+    int step(float dt) override
+    {
+        const int n_max = cells.n_max;
+        if (!seeded) {
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, model_stream()>>>(
+                n_max, seed, d_state);
+            seeded = true;
+        }
+        bind();
+#ifdef YALLA_B200
+        if (prolif_rate > 0 && reproducible) {
+            auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
+                                 Po_cell* d_dX) { reset_counters(n); };
+            cells.take_step<models::relu_w_epithelium>(dt, reset_nbs);
+            if (!division)
+                division.reset(new Cell_division<Po_cell>(n_max, seed));
+            cudaMemcpyToSymbolAsync(models::d_prolif_rate, &prolif_rate,
+                sizeof(float), 0, cudaMemcpyHostToDevice, model_stream());
+            division->divide<models::growth_division_rate, models::growth_inherit>(
+                cells, mean_dist);
+            return 0;
+        }
+        // The whole iteration -- both Heun stages with the counter resets as
+        // (capturable) generic force, then the division kernels -- is recorded
+        // once per (dt, parameters) on a side stream, with the solver issuing
+        // its stages into the recording, and replayed with one graph launch.
+        // reset_counters is handed n_max there: clearing the counters of dead
+        // slots as well is harmless. The first iteration runs directly (kernel
+        // attributes are set up outside any recording).
+        if (yb::graphs_enabled() && !profiling_sweeps && warmed_up) {
+            if (iteration == nullptr || iteration_dt != dt) record_iteration(dt);
+            cudaGraphLaunch(iteration, model_stream());
+            return 0;
+        }
+        warmed_up = true;
+#endif
+        enqueue_iteration(dt);
         return 0;
     }
+
+#ifdef YALLA_B200
+    cudaGraphExec_t iteration = nullptr;
+    float iteration_dt = 0.f;
+    bool warmed_up = false;
+    cudaStream_t recording_stream = nullptr;
+
+    void drop_iteration()
+    {
+        if (iteration == nullptr) return;
+        cudaStreamSynchronize(model_stream());
+        cudaGraphExecDestroy(iteration);
+        iteration = nullptr;
+    }
+    void record_iteration(float dt)
+    {
+        drop_iteration();
+        if (recording_stream == nullptr)
+            cudaStreamCreateWithFlags(&recording_stream, cudaStreamNonBlocking);
+        const cudaStream_t users = cells.stream;
+        cudaGraph_t graph;
+        cudaStreamBeginCapture(recording_stream, cudaStreamCaptureModeRelaxed);
+        cells.stream = recording_stream;
+        enqueue_iteration(dt);
+        cells.stream = users;
+        cudaStreamEndCapture(recording_stream, &graph);
+        cudaGraphInstantiate(&iteration, graph, 0);
+        cudaGraphDestroy(graph);
+        iteration_dt = dt;
+    }
+#endif
 };
 
 // ---- 7-float branching cell --------------------------------------------------------
 struct Branching_sim : Typed_sim<models::Cell> {
     Branching_sim(int n_max, int grid_size, float cube_size)
         : Typed_sim<models::Cell>{n_max, grid_size, cube_size}
-    {}
+    {
+#ifdef YALLA_B200
+        // the counter reset is two cudaMemsetAsync on the step's stream
+        cells.capture_generic_forces = true;
+#endif
+    }
     int set_param(const std::string& name, double value) override
     {
         const int fixed = Base::set_fix(name, value);
@@ -657,7 +887,7 @@ struct Branching_sim : Typed_sim<models::Cell> {
     }
     int step(float dt) override
     {
-        bind();
+        this->bind();
         auto reset_nbs = [this](const int n, const models::Cell* __restrict__ d_X,
                              models::Cell* d_dX) { reset_counters(n); };
         cells.take_step<models::epi_turing_mes_noturing>(dt, reset_nbs);
@@ -836,6 +1066,11 @@ int yb_sim_get_velocities(yb_sim* sim, float* h_v, int capacity)
     return sim->get_velocities(h_v, capacity);
 }
 
+int yb_sim_set_velocities(yb_sim* sim, const float* h_v, int n)
+{
+    return sim->set_velocities(h_v, n);
+}
+
 int yb_sim_set_ints(yb_sim* sim, const char* name, const int* h_values, int n)
 {
     return sim->set_ints(name, h_values, n);
@@ -866,6 +1101,7 @@ int yb_sim_step(yb_sim* sim, float dt, int n_steps)
 int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
     long long* cell_updates_out)
 {
+    const cudaStream_t stream = sim->work_stream();
     cudaEvent_t start, stop;
     cudaEventCreate(&start);
     cudaEventCreate(&stop);
@@ -875,13 +1111,13 @@ int yb_sim_step_timed(yb_sim* sim, float dt, int n_steps, float* ms_out,
     cudaMallocHost(&h_counts, sizeof(int) * static_cast<size_t>(n_steps + 1));
     const int* d_count = sim->count_on_device();
     cudaDeviceSynchronize();
-    cudaEventRecord(start, 0);
+    cudaEventRecord(start, stream);
     for (int k = 0; k < n_steps; k++) {
         cudaMemcpyAsync(
-            h_counts + k, d_count, sizeof(int), cudaMemcpyDeviceToHost, 0);
+            h_counts + k, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream);
         sim->step(dt);
     }
-    cudaEventRecord(stop, 0);
+    cudaEventRecord(stop, stream);
     cudaEventSynchronize(stop);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, start, stop);
@@ -911,6 +1147,8 @@ int yb_sim_step_host_async(yb_sim* sim, const float* h_in, int n, float dt,
 {
     return sim->step_host_async(h_in, n, dt, n_steps, h_out, out_cells, h_n_out);
 }
+
+int yb_sim_host_drain(yb_sim* sim) { return sim->host_drain(); }
 
 int yb_dd_load(yb_sim* sim, int stage, const float* X_owned,
     const float* v_owned, int n_owned, const float* X_ghost,
