@@ -1,0 +1,617 @@
+// Internal: brick decomposition of one tissue over the GPUs of a node, with the
+// halo exchange, the migration of cells and the global drift sum done by the
+// kernels themselves over peer memory (NVLink P2P) -- no NCCL call, no host
+// synchronisation and no copy engine in a step.
+//
+// ya||a is single-GPU; this is the extension BASELINE.json's
+// north_star asks for. The tissue is cut into bx * by * bz bricks along cube
+// boundaries, one process per GPU and brick. Interactions are strictly shorter
+// than cube_size, so a brick needs copies ("ghosts") of the neighbouring
+// bricks' cells within one cube of its faces, edges and corners: up to 26
+// neighbours. Every rank owns one EXCHANGE allocation that its neighbours map
+// into their address space (CUDA IPC; plain pointers inside one process):
+//
+//   [mailbox: {sum dX, n} of every rank for the drift, two parities, + flags]
+//   [flags:   one word per (neighbour, round kind)]
+//   [inboxes: per (neighbour, round kind) a header and `capacity` records]
+//
+// Round kinds: 0 / 1 = halo of the predictor / corrector stage, 2 = migration.
+// A round of rank A towards neighbour B is ONE kernel, dd_select: a stable
+// single-pass stream compaction (decoupled look-back per destination) that
+// stores the selected records straight into B's inbox over NVLink, and whose
+// last CTA -- after a system-scope fence -- stores the round's epoch into B's
+// flag word. B's stream meanwhile sits in dd_wait until its flags show the
+// epoch, then dd_append_ghosts / dd_merge read the inboxes. An inbox is
+// written again one step later; by then its owner has consumed it, because the
+// writer had to receive two later rounds from that owner first.
+//
+// The drift (mean force, solvers.cuh:241-255) is global: dd_allreduce_drift
+// stores this rank's {sum dX, n} into every rank's mailbox, waits for all
+// slots of the round and adds them in rank order -- the same bits on every rank.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "grid_build.cuh"
+#include "layout.cuh"
+#include "slab.cuh"
+
+namespace yb {
+
+constexpr int DD_MAX_PEERS = 26;
+constexpr int DD_MAX_RANKS = 64;
+constexpr int DD_ROUNDS = 3;  // halo X, halo X1, migration
+
+// direction (dx, dy, dz) in {-1, 0, 1}^3 <-> index 0..26 (13 = the brick itself)
+inline int dd_direction_index(int dx, int dy, int dz)
+{
+    return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+}
+
+// What a brick owns and who surrounds it (kernel argument, by value).
+struct Dd_region {
+    float lo[3], hi[3];  // owns lo <= x < hi; -+INFINITY at the tissue's ends
+    float halo;          // width of the strip copied to a neighbour
+    int n_peers;
+    signed char dir[DD_MAX_PEERS][4];  // offset of peer p in the brick grid
+};
+
+// Where the records for every peer go (peer memory; kernel argument).
+struct Dd_outboxes {
+    float* buffer[DD_MAX_PEERS];    // header + records, in the peer's allocation
+    unsigned* flag[DD_MAX_PEERS];   // gets the round's epoch when complete
+    int capacity[DD_MAX_PEERS];
+};
+
+// This rank's own inboxes of one round kind (kernel argument).
+struct Dd_inboxes {
+    const float* buffer[DD_MAX_PEERS];
+    const unsigned* flag[DD_MAX_PEERS];
+    int n_peers;
+};
+
+struct Dd_mailbox {
+    float sums[2][DD_MAX_RANKS][4];  // [parity][rank] = {sum dX.xyz, n}
+    unsigned flag[2][DD_MAX_RANKS];
+};
+
+struct Dd_mailboxes {  // every rank's mailbox, mapped here (kernel argument)
+    Dd_mailbox* of_rank[DD_MAX_RANKS];
+};
+
+__device__ __forceinline__ void store_release_sys(unsigned* p, unsigned value)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(value)
+                 : "memory");
+}
+
+__device__ __forceinline__ unsigned load_acquire_sys(const unsigned* p)
+{
+    unsigned value;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];"
+                 : "=r"(value)
+                 : "l"(p)
+                 : "memory");
+    return value;
+}
+
+__device__ __forceinline__ unsigned long long global_nanoseconds()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *flag >= epoch. Gives up after ten seconds (a peer died): the run
+// is then wrong, which `problems` reports, but the GPU does not hang.
+__device__ __forceinline__ bool wait_for_epoch(const unsigned* flag, unsigned epoch)
+{
+    const unsigned long long start = global_nanoseconds();
+    while (static_cast<int>(load_acquire_sys(flag) - epoch) < 0) {
+        if (global_nanoseconds() - start > 10000000000ull) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// Which peers get a copy of (halo round) or take over (migration round) a cell
+// at position x: bit p of the result. A peer in direction d gets the cell if
+// the cell is within the halo of (resp. beyond) the face towards d on every
+// axis where d is not 0; in a migration round the axes where d is 0 must be
+// inside, so that exactly one peer takes the cell.
+__device__ __forceinline__ unsigned dd_destinations(
+    const float* x, const Dd_region& region, bool migration)
+{
+    bool below[3], above[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float inset = migration ? 0.f : region.halo;
+        below[a] = x[a] < region.lo[a] + inset;
+        above[a] = x[a] >= region.hi[a] - inset;
+    }
+    unsigned mask = 0;
+    for (int p = 0; p < region.n_peers; p++) {
+        bool takes = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int d = region.dir[p][a];
+            if (d < 0) takes = takes && below[a];
+            if (d > 0) takes = takes && above[a];
+            if (d == 0 && migration) takes = takes && !below[a] && !above[a];
+        }
+        mask |= (takes ? 1u : 0u) << p;
+    }
+    return mask;
+}
+
+// One round towards all peers. Walks the owned cells (or, in a migration
+// round with `order`, every slot of the cube-ordered pos4 plane of the last
+// force evaluation -- the cells that stay are then re-stored in cube order,
+// see slab.cuh), ranks every cell in the list of each peer it goes to, and
+// writes the records to their final places in the peers' inboxes.
+// status: (DD_MAX_PEERS + 1) * n_tiles look-back words (last list: ghosts met
+// while walking `order`).
+template<typename Pt>
+__global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
+    Step_ctl* scan_ctl, const Pt* __restrict__ P, const float3* __restrict__ v,
+    Dd_region region, Dd_outboxes to, int migration, Pt* __restrict__ X_tmp,
+    float3* __restrict__ v_tmp, int* n_stay, unsigned long long* status,
+    int n_tiles, const float4* __restrict__ order,
+    const int* __restrict__ d_n_total, int n_max, unsigned epoch)
+{
+    constexpr int W = Layout<Pt>::lanes + 3;
+    constexpr int WARPS = SCAN_THREADS / 32;
+    constexpr int LISTS = DD_MAX_PEERS + 1;
+    __shared__ int s_tile;
+    __shared__ unsigned short s_count[LISTS][SELECT_SUB][WARPS];  // then: prefixes
+    __shared__ int s_total[LISTS];
+    __shared__ int s_tile_prefix[LISTS];
+
+    const int t = threadIdx.x;
+    const int lane_id = t & 31, warp_id = t >> 5;
+    if (t == 0) s_tile = atomicAdd(&scan_ctl->scan_next_tile, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const unsigned scan_epoch =
+        static_cast<unsigned>(*(volatile int*)&scan_ctl->scan_epoch) & 0x3fffffffu;
+    const int n_owned = ctl->n_owned;
+    const bool permute = order != nullptr;
+    const int n = permute ? live_cells(d_n_total, n_max) : n_owned;
+    const int first = tile * SCAN_TILE;
+    const int n_peers = region.n_peers;
+    const int n_lists = n_peers + (permute ? 1 : 0);
+
+    unsigned mask[SELECT_SUB];  // bit p: goes to peer p; bit 31: a ghost entry
+    int cell[SELECT_SUB];
+#pragma unroll
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int q = first + u * SCAN_THREADS + t;
+        mask[u] = 0;
+        cell[u] = q;
+        if (q < n) {
+            bool ghost = false;
+            if (permute) {
+                cell[u] = __float_as_int(__ldg(&order[q].w));
+                ghost = cell[u] >= n_owned;
+            }
+            if (ghost) {
+                mask[u] = 1u << 31;
+            } else {
+                const float* x = reinterpret_cast<const float*>(P + cell[u]);
+                const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
+                mask[u] = dd_destinations(pos, region, migration != 0);
+            }
+        }
+        for (int l = 0; l < n_lists; l++) {
+            const unsigned bit = l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
+            const unsigned votes = __ballot_sync(0xffffffffu, bit);
+            if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the SUB x WARPS counts of every list, one warp per list
+    for (int l = warp_id; l < n_lists; l += WARPS) {
+        constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
+        unsigned short* counts = &s_count[l][0][0];
+        int mine[PER_LANE], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            mine[q] = counts[lane_id * PER_LANE + q];
+            sum += mine[q];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_id >= d) incl += up;
+        }
+        int running = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            counts[lane_id * PER_LANE + q] = running;
+            running += mine[q];
+        }
+        const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
+        const int exclusive = scan_lookback(
+            status + size_t(l) * n_tiles, tile, scan_epoch, aggregate, lane_id);
+        if (lane_id == 0) {
+            s_total[l] = aggregate;
+            s_tile_prefix[l] = exclusive;
+        }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int q = first + u * SCAN_THREADS + t;
+        const int i = cell[u];
+        const unsigned below = (1u << lane_id) - 1u;
+        int leavers_before = 0;  // over all peers (migration: one peer per cell)
+        for (int p = 0; p < n_peers; p++) {
+            const unsigned bit = (mask[u] >> p) & 1u;
+            const unsigned votes = __ballot_sync(0xffffffffu, bit);
+            const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
+                           __popc(votes & below);
+            leavers_before += at;
+            if (bit && at < to.capacity[p])
+                write_record(to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
+        }
+        int ghosts_before = 0;
+        if (permute) {
+            const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
+            ghosts_before = s_tile_prefix[n_peers] +
+                            s_count[n_peers][u][warp_id] + __popc(votes & below);
+        }
+        if (migration && q < n && mask[u] == 0) {
+            const int at = q - leavers_before - ghosts_before;
+            store_pt(X_tmp, at, load_pt(P, i));
+            v_tmp[at] = v[i];
+        }
+    }
+
+    // the tile that holds the last entry knows the totals
+    const int last_tile = n > 0 ? (n - 1) / SCAN_TILE : 0;
+    if (tile == last_tile && t < 32) {
+        int leaving = 0;
+        for (int p = t; p < n_peers; p += 32) {
+            const int total = s_tile_prefix[p] + s_total[p];
+            if (total > to.capacity[p]) atomicAdd(&ctl->out_of_grid, 1 << 20);
+            to.buffer[p][0] = __int_as_float(min(total, to.capacity[p]));
+            leaving += total;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            leaving += __shfl_xor_sync(0xffffffffu, leaving, d);
+        if (migration && t == 0) *n_stay = n_owned - leaving;
+    }
+    // Everything this CTA stored in peer memory must be visible system-wide
+    // before the epoch; the last CTA to finish publishes it and re-arms the scan.
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        if (atomicAdd(&scan_ctl->scan_tiles_done, 1) == n_tiles - 1) {
+            scan_ctl->scan_next_tile = 0;
+            scan_ctl->scan_tiles_done = 0;
+            scan_ctl->scan_epoch =
+                static_cast<int>((scan_epoch + 1u) & 0x3fffffffu);
+            __threadfence_system();
+            for (int p = 0; p < n_peers; p++) store_release_sys(to.flag[p], epoch);
+        }
+    }
+}
+
+// Holds the stream until every inbox of the round shows the epoch.
+__global__ void dd_wait(Step_ctl* ctl, Dd_inboxes in, unsigned epoch)
+{
+    const int p = threadIdx.x;
+    if (p < in.n_peers && !wait_for_epoch(in.flag[p], epoch))
+        atomicAdd(&ctl->out_of_grid, 1 << 24);
+}
+
+// Number of records in every inbox and where each starts in the concatenation;
+// room for at most `room` records in total.
+__device__ __forceinline__ int dd_inbox_layout(
+    const Dd_inboxes& in, int room, int* start)
+{
+    int total = 0;
+    for (int p = 0; p < in.n_peers; p++) {
+        start[p] = total;
+        int count = __float_as_int(in.buffer[p][0]);
+        count = max(0, min(count, room - total));
+        total += count;
+    }
+    start[in.n_peers] = total;
+    return total;
+}
+
+// Ghosts: append the received records behind the owned cells of P (X or X1)
+// and set the total cell count. Order: by peer, then as ranked by the sender.
+template<typename Pt>
+__global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
+    float3* v, Dd_inboxes in, int n_max, int* d_n)
+{
+    constexpr int W = Layout<Pt>::lanes + 3;
+    __shared__ int s_start[DD_MAX_PEERS + 1];
+    const int n = ctl->n_owned;
+    if (threadIdx.x == 0) dd_inbox_layout(in, n_max - n, s_start);
+    __syncthreads();
+    const int total = s_start[in.n_peers];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total;
+         r += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (r >= s_start[p + 1]) p++;
+        read_record(in.buffer[p] + SLAB_HEADER + size_t(r - s_start[p]) * W, P, v,
+            n + r);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_n = n + total;
+}
+
+// Migration, step 2: owned cells := stayers, then the arrivals peer by peer.
+template<typename Pt>
+__global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
+    const int* __restrict__ n_stay_in, const Pt* __restrict__ X_tmp,
+    const float3* __restrict__ v_tmp, Dd_inboxes in, int n_max, Pt* X, float3* v,
+    int* new_count)
+{
+    constexpr int W = Layout<Pt>::lanes + 3;
+    __shared__ int s_start[DD_MAX_PEERS + 1];
+    const int n_stay = *n_stay_in;
+    if (threadIdx.x == 0) dd_inbox_layout(in, n_max - n_stay, s_start);
+    __syncthreads();
+    const int total = n_stay + s_start[in.n_peers];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total;
+         r += gridDim.x * blockDim.x) {
+        if (r < n_stay) {
+            store_pt(X, r, load_pt(X_tmp, r));
+            v[r] = v_tmp[r];
+        } else {
+            const int a = r - n_stay;
+            int p = 0;
+            while (a >= s_start[p + 1]) p++;
+            read_record(in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W, X,
+                v, r);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = total;
+}
+
+// Global drift of a stage: publish {sum dX, n} of the owned cells to every
+// rank, wait for everybody's, add in rank order, divide like operator/= would
+// (dtypes.cuh:204-208). One warp per 32 ranks; launched <<<1, DD_MAX_RANKS>>>.
+__global__ void dd_allreduce_drift(Step_ctl* ctl, int stage, Dd_mailboxes boxes,
+    const Dd_mailbox* mine, int rank, int world, int parity, unsigned epoch)
+{
+    __shared__ float s_sums[DD_MAX_RANKS][4];
+    const int r = threadIdx.x;
+    if (r < world) {
+        Dd_mailbox* theirs = boxes.of_rank[r];
+        float4 sums;
+        sums.x = ctl->drift_sum[stage][0], sums.y = ctl->drift_sum[stage][1];
+        sums.z = ctl->drift_sum[stage][2], sums.w = ctl->drift_sum[stage][3];
+        *reinterpret_cast<float4*>(theirs->sums[parity][rank]) = sums;
+        __threadfence_system();
+        store_release_sys(&theirs->flag[parity][rank], epoch);
+        if (!wait_for_epoch(&mine->flag[parity][r], epoch))
+            atomicAdd(&ctl->out_of_grid, 1 << 24);
+        const volatile float* got = mine->sums[parity][r];
+        s_sums[r][0] = got[0], s_sums[r][1] = got[1];
+        s_sums[r][2] = got[2], s_sums[r][3] = got[3];
+    }
+    __syncthreads();
+    if (r == 0) {
+        float total[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < world; q++)
+            for (int c = 0; c < 4; c++) total[c] += s_sums[q][c];
+        const float inv_n = static_cast<float>(1. / total[3]);
+        ctl->drift[stage][0] = total[0] * inv_n;
+        ctl->drift[stage][1] = total[1] * inv_n;
+        ctl->drift[stage][2] = total[2] * inv_n;
+    }
+}
+
+// ---- a seeded tissue generated in place ---------------------------------------
+// The cells of a jittered FCC ball (nearest-neighbour distance d, radius R)
+// that fall into this brick, written behind *d_count. Every lattice site gets
+// its jitter from a hash of (site, seed), so the tissue is the same however it
+// is cut; only the order of the cells in memory depends on the cut and on
+// atomic timing (a decomposed run re-stores its cells in cube order anyway).
+__device__ __forceinline__ unsigned long long dd_mix(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+template<typename Pt>
+__global__ void __launch_bounds__(256) dd_seed_lattice_ball(float radius, float d,
+    float jitter, unsigned long long seed, Dd_region region, int half,
+    long long n_sites, int n_max, Pt* X, float3* v, int* d_count)
+{
+    const float a = d * 1.41421356237f;  // conventional FCC cell edge
+    const int side = 2 * half + 1;
+    for (long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+         s < n_sites; s += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int basis = static_cast<int>(s & 3);
+        long long c = s >> 2;
+        const int ix = static_cast<int>(c % side) - half;
+        c /= side;
+        const int iy = static_cast<int>(c % side) - half;
+        const int iz = static_cast<int>(c / side) - half;
+        float x = ix * a, y = iy * a, z = iz * a;
+        if (basis == 1) x += 0.5f * a, y += 0.5f * a;
+        if (basis == 2) x += 0.5f * a, z += 0.5f * a;
+        if (basis == 3) y += 0.5f * a, z += 0.5f * a;
+        if (x * x + y * y + z * z > radius * radius) continue;
+        const unsigned long long h1 = dd_mix(seed ^ (static_cast<unsigned long long>(s) * 3 + 1));
+        const unsigned long long h2 = dd_mix(h1);
+        const float scale = 2.f * jitter * d;
+        x += ((h1 & 0xffffff) * (1.f / 16777216.f) - 0.5f) * scale;
+        y += (((h1 >> 24) & 0xffffff) * (1.f / 16777216.f) - 0.5f) * scale;
+        z += ((h2 & 0xffffff) * (1.f / 16777216.f) - 0.5f) * scale;
+        const float pos[3] = {x, y, z};
+        bool mine = true;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            mine = mine && pos[q] >= region.lo[q] && pos[q] < region.hi[q];
+        if (!mine) continue;
+        const int slot = atomicAdd(d_count, 1);
+        if (slot >= n_max) continue;  // reported through the count
+        Pt cell{0};
+        cell.x = x, cell.y = y, cell.z = z;
+        store_pt(X, slot, cell);
+        v[slot] = float3{0.f, 0.f, 0.f};
+    }
+}
+
+// ---- host side: the exchange allocation and its layout -------------------------
+struct Domain_link {
+    bool active = false;
+    int rank = 0, world = 1;
+    Dd_region region{};
+    int peer_rank[DD_MAX_PEERS] = {};
+    int peer_direction[DD_MAX_PEERS] = {};  // direction index 0..26 of peer p
+    int capacity[DD_MAX_PEERS] = {};
+    int record_floats = 0;
+
+    unsigned char* base = nullptr;  // this rank's exchange allocation
+    size_t bytes = 0;
+    size_t inbox_offset[DD_MAX_PEERS][DD_ROUNDS] = {};
+    size_t flag_offset[DD_MAX_PEERS][DD_ROUNDS] = {};
+
+    Dd_outboxes out[DD_ROUNDS] = {};  // filled by connect()
+    Dd_mailboxes mailboxes{};
+    unsigned epoch[DD_ROUNDS] = {0, 0, 0};
+    unsigned drift_epoch = 0;
+
+    // scratch of dd_select
+    int n_tiles = 0;
+    unsigned long long* status = nullptr;
+    Step_ctl* scan_ctl = nullptr;
+    int* n_stay = nullptr;
+    int* new_count = nullptr;
+    bool permute = true;
+
+    static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+    void begin(int rank_, int world_, const Dd_region& region_,
+        const int* peer_ranks27, const int* capacity27, int record_floats_,
+        int n_max)
+    {
+        release();
+        rank = rank_, world = world_, region = region_;
+        record_floats = record_floats_;
+        region.n_peers = 0;
+        for (int dir = 0; dir < 27; dir++) {
+            if (dir == 13 || peer_ranks27[dir] < 0) continue;
+            const int p = region.n_peers++;
+            peer_rank[p] = peer_ranks27[dir];
+            peer_direction[p] = dir;
+            capacity[p] = capacity27[dir];
+            region.dir[p][0] = static_cast<signed char>(dir % 3 - 1);
+            region.dir[p][1] = static_cast<signed char>((dir / 3) % 3 - 1);
+            region.dir[p][2] = static_cast<signed char>(dir / 9 - 1);
+            region.dir[p][3] = 0;
+        }
+        size_t at = align_up(sizeof(Dd_mailbox));
+        for (int p = 0; p < region.n_peers; p++)
+            for (int q = 0; q < DD_ROUNDS; q++) {
+                flag_offset[p][q] = at;
+                at += sizeof(unsigned);
+            }
+        at = align_up(at);
+        for (int p = 0; p < region.n_peers; p++)
+            for (int q = 0; q < DD_ROUNDS; q++) {
+                inbox_offset[p][q] = at;
+                at = align_up(at + sizeof(float) * (SLAB_HEADER +
+                                        size_t(capacity[p]) * record_floats));
+            }
+        bytes = at;
+        YB_CUDA(cudaMalloc(&base, bytes));
+        YB_CUDA(cudaMemset(base, 0, bytes));
+        for (int r = 0; r < DD_MAX_RANKS; r++) mailboxes.of_rank[r] = nullptr;
+        mailboxes.of_rank[rank] = reinterpret_cast<Dd_mailbox*>(base);
+
+        n_tiles = ceil_div(n_max > 0 ? n_max : 1, SCAN_TILE);
+        const size_t words = size_t(DD_MAX_PEERS + 1) * n_tiles;
+        YB_CUDA(cudaMalloc(&status, words * sizeof(unsigned long long)));
+        YB_CUDA(cudaMemset(status, 0, words * sizeof(unsigned long long)));
+        YB_CUDA(cudaMalloc(&scan_ctl, sizeof(Step_ctl)));
+        Step_ctl fresh{};
+        fresh.scan_epoch = 1;
+        YB_CUDA(cudaMemcpy(scan_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        YB_CUDA(cudaMalloc(&n_stay, sizeof(int)));
+        YB_CUDA(cudaMalloc(&new_count, sizeof(int)));
+        const char* env = getenv("YALLA_B200_SLAB_PERMUTE");
+        permute = !(env && env[0] == '0');
+        for (int q = 0; q < DD_ROUNDS; q++) epoch[q] = 0;
+        drift_epoch = 0;
+        active = true;
+    }
+
+    int peer_of_direction(int dir) const
+    {
+        for (int p = 0; p < region.n_peers; p++)
+            if (peer_direction[p] == dir) return p;
+        return -1;
+    }
+
+    // The peer in direction `dir` keeps my records in ITS inboxes for the
+    // opposite direction: peer_base is its exchange allocation as mapped here,
+    // offsets6 = its {inbox_offset[q], flag_offset[q]} for direction 26 - dir.
+    bool connect(int dir, void* peer_base, const long long* offsets6)
+    {
+        const int p = peer_of_direction(dir);
+        if (p < 0) return false;
+        unsigned char* theirs = static_cast<unsigned char*>(peer_base);
+        for (int q = 0; q < DD_ROUNDS; q++) {
+            out[q].buffer[p] = reinterpret_cast<float*>(theirs + offsets6[q]);
+            out[q].flag[p] = reinterpret_cast<unsigned*>(theirs + offsets6[3 + q]);
+            out[q].capacity[p] = capacity[p];
+        }
+        return true;
+    }
+    void connect_mailbox(int r, void* peer_base)
+    {
+        mailboxes.of_rank[r] = static_cast<Dd_mailbox*>(peer_base);
+    }
+    Dd_inboxes inboxes(int q) const
+    {
+        Dd_inboxes in{};
+        in.n_peers = region.n_peers;
+        for (int p = 0; p < region.n_peers; p++) {
+            in.buffer[p] = reinterpret_cast<const float*>(base + inbox_offset[p][q]);
+            in.flag[p] = reinterpret_cast<const unsigned*>(base + flag_offset[p][q]);
+        }
+        return in;
+    }
+    const Dd_mailbox* my_mailbox() const
+    {
+        return reinterpret_cast<const Dd_mailbox*>(base);
+    }
+    bool connected() const
+    {
+        for (int p = 0; p < region.n_peers; p++)
+            if (out[0].buffer[p] == nullptr) return false;
+        for (int r = 0; r < world; r++)
+            if (mailboxes.of_rank[r] == nullptr) return false;
+        return true;
+    }
+
+    void release()
+    {
+        if (!active) return;
+        cudaFree(new_count);
+        cudaFree(n_stay);
+        cudaFree(scan_ctl);
+        cudaFree(status);
+        cudaFree(base);
+        base = nullptr;
+        active = false;
+        for (int q = 0; q < DD_ROUNDS; q++) out[q] = Dd_outboxes{};
+    }
+};
+
+}  // namespace yb

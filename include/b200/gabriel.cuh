@@ -21,7 +21,7 @@ template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
 __global__ void __launch_bounds__(GABRIEL_THREADS) sweep_gabriel(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
-    const int* __restrict__ offset, float cube_size, int grid_size, int n_cubes,
+    const int* __restrict__ offset, float cube_size, Grid_box box,
     float gabriel_coefficient, Pt* d_dX, float* __restrict__ partials,
     int stage, int drift_mode, int fix_point, Step_ctl* ctl)
 {
@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(GABRIEL_THREADS) sweep_gabriel(
 
             // 1. every cell within cube_size, in the reference's sweep order
             for (int r = 0; r < SWEEP_ROWS; r++) {
-                const int c = my_cube + row_shift(r, grid_size);
-                const int lo = __ldg(offset + clamp_cube(c - 1, n_cubes));
-                const int hi = __ldg(offset + clamp_cube(c + 2, n_cubes));
+                const int c = my_cube + row_shift(r, box);
+                const int lo = __ldg(offset + clamp_cube(c - 1, box.n_cubes));
+                const int hi = __ldg(offset + clamp_cube(c + 2, box.n_cubes));
                 for (int q = lo; q < hi; q++) {
                     const float4 pj = __ldg(pos4 + q);
                     // r = Xi - Xj lane-wise: x - x', as in operator-
@@ -155,8 +155,9 @@ protected:
     // both knobs are baked into captured graphs
     yb::Graph_key graph_key() const
     {
-        return yb::Graph_key{this->cube_size, gabriel_coefficient, this->z_half,
-            this->active_cubes};
+        return yb::Graph_key{this->cube_size, gabriel_coefficient,
+            (this->box.z_half * 1024 + this->box.y_half) * 1024 + this->box.x_half,
+            this->box.n_cubes};
     }
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
@@ -181,7 +182,7 @@ protected:
         yb::sweep_gabriel<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::GABRIEL_THREADS, 0, s>>>(d_n, this->n_max, this->pos4,
                 this->aux, this->cube_sorted, this->sort.offset, this->cube_size,
-                this->grid_size, this->active_cubes, gabriel_coefficient, d_dX,
+                this->box, gabriel_coefficient, d_dX,
                 d_partials, stage, drift_mode, fix_point, d_ctl);
     }
 };

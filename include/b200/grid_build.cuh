@@ -110,27 +110,58 @@ inline Stage_context*& current_stage()
 }
 
 // ---- cube ids ---------------------------------------------------------------
+// The solver's grid. By default the reference's: grid_size^3 cubes around the
+// origin (solvers.cuh:357-360). One domain of a decomposed tissue restricts it
+// to the box of cubes it can touch -- nx * ny * nz cubes starting at cube
+// (grid_size / 2 - x_half, ...) of that cubic grid -- so that the per-cube
+// tables, and the scan over them, stay proportional to the domain.
+struct Grid_box {
+    int nx, ny, nz;                // cubes along each axis
+    int x_half, y_half, z_half;    // ix = floor(x / cube_size) + x_half, ...
+    int n_cubes;                   // nx * ny * nz
+    int restricted;                // 0: the reference's cubic grid
+
+    static Grid_box cubic(int grid_size)
+    {
+        return Grid_box{grid_size, grid_size, grid_size, grid_size / 2,
+            grid_size / 2, grid_size / 2, grid_size * grid_size * grid_size, 0};
+    }
+    bool operator==(const Grid_box& o) const
+    {
+        return nx == o.nx && ny == o.ny && nz == o.nz && x_half == o.x_half &&
+               y_half == o.y_half && z_half == o.z_half;
+    }
+};
+
 // Integer restatement of solvers.cuh:357-360. The reference evaluates
 // floor(x / cs) + gs / 2 + (...) * gs + (...) * gs * gs in FP32, which is exact
 // (hence equal to this) while all partial sums stay below 2^24, i.e. for
 // grid_size <= 256. x / cs must stay an IEEE division: the
 // cube of a cell within an ulp of a face depends on it.
 // Ids outside [0, n_cubes) trip D_ASSERT in the reference; here they are
-// clamped into the grid and counted.
-// z_half is grid_size / 2 for the reference's cubic grid; a slab of a
-// decomposed domain (b200/slab.cuh) numbers its z layers from its own lower
-// end instead and has n_cubes = grid_size^2 * (its layers).
+// clamped into the grid and counted. In a restricted box every axis is
+// checked on its own (a cell beyond the box in x must not wrap into the next
+// row); the cubic grid keeps the reference's linear rule.
 __device__ __forceinline__ int cube_of(float x, float y, float z,
-    float cube_size, int grid_size, int z_half, int n_cubes, int* out_of_grid)
+    float cube_size, const Grid_box& box, int* out_of_grid)
 {
-    const long long half = grid_size / 2;
-    const long long ix = static_cast<long long>(floorf(x / cube_size)) + half;
-    const long long iy = static_cast<long long>(floorf(y / cube_size)) + half;
-    const long long iz = static_cast<long long>(floorf(z / cube_size)) + z_half;
-    long long id = ix + iy * grid_size + iz * grid_size * grid_size;
-    if (id < 0 || id >= n_cubes) {
+    long long ix = static_cast<long long>(floorf(x / cube_size)) + box.x_half;
+    long long iy = static_cast<long long>(floorf(y / cube_size)) + box.y_half;
+    long long iz = static_cast<long long>(floorf(z / cube_size)) + box.z_half;
+    if (box.restricted) {
+        const bool outside = ix < 0 || ix >= box.nx || iy < 0 || iy >= box.ny ||
+                             iz < 0 || iz >= box.nz;
+        if (outside) {
+            if (out_of_grid) atomicAdd(out_of_grid, 1);
+            ix = ix < 0 ? 0 : (ix >= box.nx ? box.nx - 1 : ix);
+            iy = iy < 0 ? 0 : (iy >= box.ny ? box.ny - 1 : iy);
+            iz = iz < 0 ? 0 : (iz >= box.nz ? box.nz - 1 : iz);
+        }
+    }
+    long long id = ix + iy * box.nx + iz * box.nx * box.ny;
+    if (id < 0 || id >= box.n_cubes) {
         if (out_of_grid) atomicAdd(out_of_grid, 1);  // nullptr: just recompute
-        id = id < 0 ? 0 : n_cubes - 1;
+        id = id < 0 ? 0 : box.n_cubes - 1;
     }
     return static_cast<int>(id);
 }
@@ -145,16 +176,15 @@ __device__ __forceinline__ int live_cells(const int* d_n, int n_max)
 // its update kernel for the second stage).
 template<typename Pt>
 __global__ void __launch_bounds__(256) bin_cells(const int* __restrict__ d_n,
-    int n_max, const Pt* __restrict__ d_X, float cube_size, int grid_size,
-    int z_half, int n_cubes, int* __restrict__ key, int* __restrict__ arrival,
-    int* count, Step_ctl* ctl)
+    int n_max, const Pt* __restrict__ d_X, float cube_size, Grid_box box,
+    int* __restrict__ key, int* __restrict__ arrival, int* count, Step_ctl* ctl)
 {
     const int n = live_cells(d_n, n_max);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += gridDim.x * blockDim.x) {
         const float* p = reinterpret_cast<const float*>(d_X + i);
         const int c = cube_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), cube_size,
-            grid_size, z_half, n_cubes, &ctl->out_of_grid);
+            box, &ctl->out_of_grid);
         key[i] = c;
         arrival[i] = atomicAdd(count + c, 1);
     }
@@ -445,8 +475,8 @@ __global__ void __launch_bounds__(256) place_cells(
 template<typename Pt>
 __global__ void __launch_bounds__(256) settle_cells(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ staged,
-    const int* __restrict__ offset, float cube_size, int grid_size, int z_half,
-    int n_cubes, float4* __restrict__ pos4, float4* __restrict__ aux,
+    const int* __restrict__ offset, float cube_size, Grid_box box,
+    float4* __restrict__ pos4, float4* __restrict__ aux,
     int* __restrict__ cube_sorted)
 {
     using L = Layout<Pt>;
@@ -456,8 +486,7 @@ __global__ void __launch_bounds__(256) settle_cells(
          k += gridDim.x * blockDim.x) {
         const float4 me = __ldg(staged + size_t(k) * REC);
         // same arithmetic as the binning, so the same cube
-        const int c = cube_of(
-            me.x, me.y, me.z, cube_size, grid_size, z_half, n_cubes, nullptr);
+        const int c = cube_of(me.x, me.y, me.z, cube_size, box, nullptr);
         const int start = __ldg(offset + c), end = __ldg(offset + c + 1);
         const int id = __float_as_int(me.w);
         int rank = 0;

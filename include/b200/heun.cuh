@@ -27,9 +27,8 @@ template<typename Pt, bool BIN>
 __global__ void __launch_bounds__(256) predictor_step(
     const int* __restrict__ d_n, int n_max, float dt,
     const Pt* __restrict__ d_X, const Pt* __restrict__ d_dX,
-    Pt* __restrict__ d_X1, Step_ctl* ctl, float cube_size, int grid_size,
-    int z_half, int n_cubes, int* __restrict__ key, int* __restrict__ arrival,
-    int* count)
+    Pt* __restrict__ d_X1, Step_ctl* ctl, float cube_size, Grid_box box,
+    int* __restrict__ key, int* __restrict__ arrival, int* count)
 {
     const int n = live_cells(d_n, n_max);
     const float fx = ctl->drift[0][0], fy = ctl->drift[0][1],
@@ -43,8 +42,8 @@ __global__ void __launch_bounds__(256) predictor_step(
         const Pt X1 = load_pt(d_X, i) + dX * dt;
         store_pt(d_X1, i, X1);
         if (BIN) {
-            const int c = cube_of(X1.x, X1.y, X1.z, cube_size, grid_size,
-                z_half, n_cubes, &ctl->out_of_grid);
+            const int c = cube_of(
+                X1.x, X1.y, X1.z, cube_size, box, &ctl->out_of_grid);
             key[i] = c;
             arrival[i] = atomicAdd(count + c, 1);
         }

@@ -152,12 +152,12 @@ __device__ __forceinline__ int listed_at(uint32_t next_entry, uint32_t column)
 // Same ordering as the reference's d_nhood table (solvers.cuh:472-484): the
 // y-shift cycles 0, -1, +1 fastest, the z-shift 0, -1, +1 slowest; inside a row
 // x runs -1, 0, +1, which is simply "the three adjacent ids".
-__device__ __forceinline__ int row_shift(int r, int grid_size)
+__device__ __forceinline__ int row_shift(int r, const Grid_box& box)
 {
     const int ry = r % 3, rz = r / 3;
     const int dy = ry == 0 ? 0 : (ry == 1 ? -1 : 1);
     const int dz = rz == 0 ? 0 : (rz == 1 ? -1 : 1);
-    return dy * grid_size + dz * grid_size * grid_size;
+    return dy * box.nx + dz * box.nx * box.ny;
 }
 
 // Cube ids stay far below 2^30 (grid_size <= 1024), so id +- one z-layer fits
@@ -173,7 +173,7 @@ __device__ __forceinline__ int clamp_cube(int c, int n_cubes)
 // they are consistent with the binning. A cell whose cube id was clamped (out
 // of the grid) is not where its id says: no trimming for it.
 __device__ __forceinline__ void trim_gaps(const float4& me, float cube_size,
-    int grid_size, int z_half, int my_cube, float (*gap2)[3])
+    const Grid_box& box, int my_cube, float (*gap2)[3])
 {
     const float q[3] = {me.x / cube_size, me.y / cube_size, me.z / cube_size};
     float fl[3];
@@ -187,11 +187,10 @@ __device__ __forceinline__ void trim_gaps(const float4& me, float cube_size,
         gap2[c][1] = below * below;
         gap2[c][2] = above * above;
     }
-    const long long half = grid_size / 2;
-    const long long id = (static_cast<long long>(fl[0]) + half) +
-                         (static_cast<long long>(fl[1]) + half) * grid_size +
-                         (static_cast<long long>(fl[2]) + z_half) *
-                             grid_size * grid_size;
+    const long long id = (static_cast<long long>(fl[0]) + box.x_half) +
+                         (static_cast<long long>(fl[1]) + box.y_half) * box.nx +
+                         (static_cast<long long>(fl[2]) + box.z_half) *
+                             box.nx * box.ny;
     if (id != my_cube) {
 #pragma unroll
         for (int c = 0; c < 3; c++) gap2[c][1] = gap2[c][2] = 0.f;
@@ -344,9 +343,9 @@ __global__ void __launch_bounds__(
     SWEEP_THREADS, Sweep_config<Layout<Pt>::lanes>::min_ctas) sweep_cubes(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ cube_sorted,
-    const int* __restrict__ offset, float cube_size, int grid_size, int z_half,
-    int n_cubes, Pt* d_dX, float* __restrict__ partials, int stage,
-    int drift_mode, int fix_point, Step_ctl* ctl, int only_if_overflow)
+    const int* __restrict__ offset, float cube_size, Grid_box box, Pt* d_dX,
+    float* __restrict__ partials, int stage, int drift_mode, int fix_point,
+    Step_ctl* ctl, int only_if_overflow)
 {
     using L = Layout<Pt>;
     // behind list_cubes + interact_lists: only if a neighbour list overflowed
@@ -381,11 +380,11 @@ __global__ void __launch_bounds__(
 
         if (t < SWEEP_ROWS) {
             const int last_slot = min(first_slot + SWEEP_THREADS, n) - 1;
-            const int shift = row_shift(t, grid_size);
+            const int shift = row_shift(t, box);
             const int lo = __ldg(offset +
-                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, n_cubes));
+                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, box.n_cubes));
             const int hi = __ldg(offset +
-                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, n_cubes));
+                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, box.n_cubes));
             s_row_lo[t] = lo;
             s_row_v[t + 1] = hi > lo ? hi - lo : 0;  // length, scanned below
         }
@@ -403,17 +402,17 @@ __global__ void __launch_bounds__(
         // That drops about a quarter of the candidates (corner cubes half of
         // the time, edge cubes a fifth) and never a pair the exact test accepts.
         float gap2[3][3];  // [axis][0: same, 1: -1, 2: +1], in cube_size^2
-        trim_gaps(me, cube_size, grid_size, z_half, my_cube, gap2);
+        trim_gaps(me, cube_size, box, my_cube, gap2);
         int my_lo[SWEEP_ROWS], my_hi[SWEEP_ROWS];
 #pragma unroll
         for (int r = 0; r < SWEEP_ROWS; r++) {
-            const int c = my_cube + row_shift(r, grid_size);
+            const int c = my_cube + row_shift(r, box);
             const float row_gap2 = gap2[1][r % 3] + gap2[2][r / 3];
             const bool row_out = !live || row_gap2 >= SWEEP_TRIM_LIMIT;
             const int first = row_gap2 + gap2[0][1] >= SWEEP_TRIM_LIMIT ? c : c - 1;
             const int last = row_gap2 + gap2[0][2] >= SWEEP_TRIM_LIMIT ? c + 1 : c + 2;
-            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, n_cubes));
-            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, n_cubes));
+            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, box.n_cubes));
+            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, box.n_cubes));
         }
         __syncthreads();
         if (t == 0) {
@@ -601,9 +600,9 @@ struct List_config {  // list_cubes: the float3 budget of the fused sweep
 __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
     list_cubes(const int* __restrict__ d_n, int n_max,
         const float4* __restrict__ pos4, const int* __restrict__ cube_sorted,
-        const int* __restrict__ offset, float cube_size, int grid_size,
-        int z_half, int n_cubes, int* __restrict__ nb,
-        int* __restrict__ nb_count, int nb_stride, Step_ctl* ctl)
+        const int* __restrict__ offset, float cube_size, Grid_box box,
+        int* __restrict__ nb, int* __restrict__ nb_count,
+        unsigned char* __restrict__ nb_order, int nb_stride, Step_ctl* ctl)
 {
     constexpr int SWEEP_STAGE_CAP = List_config::stage_cap;
     constexpr int SWEEP_LIST_CAP = List_config::list_cap;
@@ -615,6 +614,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
     __shared__ int s_row_lo[SWEEP_ROWS];
     __shared__ int s_row_v[SWEEP_ROWS + 1];
     __shared__ __align__(8) uint64_t s_bar;
+    // balancing of interact_lists: cells per list length, per warp
+    __shared__ unsigned char s_hist[SWEEP_THREADS / 32][LIST_MAX + 1];
+    __shared__ unsigned char s_longer[LIST_MAX + 2];
 
     const int t = threadIdx.x;
     const int n = live_cells(d_n, n_max);
@@ -633,14 +635,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
 
         if (t < SWEEP_ROWS) {
             const int last_slot = min(first_slot + SWEEP_THREADS, n) - 1;
-            const int shift = row_shift(t, grid_size);
+            const int shift = row_shift(t, box);
             const int lo = __ldg(offset +
-                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, n_cubes));
+                clamp_cube(__ldg(cube_sorted + first_slot) + shift - 1, box.n_cubes));
             const int hi = __ldg(offset +
-                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, n_cubes));
+                clamp_cube(__ldg(cube_sorted + last_slot) + shift + 2, box.n_cubes));
             s_row_lo[t] = lo;
             s_row_v[t + 1] = hi > lo ? hi - lo : 0;
         }
+        for (int q = t; q < (SWEEP_THREADS / 32) * (LIST_MAX + 1); q += SWEEP_THREADS)
+            (&s_hist[0][0])[q] = 0;
         float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
         int my_cube = 0;
         if (live) {
@@ -648,17 +652,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
             my_cube = __ldg(cube_sorted + k);
         }
         float gap2[3][3];
-        trim_gaps(me, cube_size, grid_size, z_half, my_cube, gap2);
+        trim_gaps(me, cube_size, box, my_cube, gap2);
         int my_lo[SWEEP_ROWS], my_hi[SWEEP_ROWS];
 #pragma unroll
         for (int r = 0; r < SWEEP_ROWS; r++) {
-            const int c = my_cube + row_shift(r, grid_size);
+            const int c = my_cube + row_shift(r, box);
             const float row_gap2 = gap2[1][r % 3] + gap2[2][r / 3];
             const bool row_out = !live || row_gap2 >= SWEEP_TRIM_LIMIT;
             const int first = row_gap2 + gap2[0][1] >= SWEEP_TRIM_LIMIT ? c : c - 1;
             const int last = row_gap2 + gap2[0][2] >= SWEEP_TRIM_LIMIT ? c + 1 : c + 2;
-            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, n_cubes));
-            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, n_cubes));
+            my_lo[r] = row_out ? 0 : __ldg(offset + clamp_cube(first, box.n_cubes));
+            my_hi[r] = row_out ? 0 : __ldg(offset + clamp_cube(last, box.n_cubes));
         }
         __syncthreads();
         if (t == 0) {
@@ -749,21 +753,98 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
         }
         if (live) nb_count[k] = n_listed;
         if (n_listed > LIST_MAX) ctl->list_overflow = 1;
+
+        // Which cell of the chunk thread q of interact_lists takes: the cells
+        // in order of DESCENDING list length (ties: ascending slot), so that
+        // the lanes of a warp walk lists of about the same length -- a warp
+        // iterates the maximum over its lanes. A stable counting sort over the
+        // (at most LIST_MAX + 1) distinct lengths.
+        const int key = min(n_listed, LIST_MAX);
+        const int lane_id = t & 31, warp_id = t >> 5;
+        const unsigned same = __match_any_sync(0xffffffffu, key);
+        if (lane_id == __ffs(same) - 1) s_hist[warp_id][key] = __popc(same);
+        __syncthreads();
+        if (t <= LIST_MAX) {  // cells per length, over the warps
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < SWEEP_THREADS / 32; w++) total += s_hist[w][t];
+            s_longer[t] = total;
+        }
+        __syncthreads();
+        if (t == 0) {  // cells with a longer list than l, for every l
+            int running = 0;
+            for (int l = LIST_MAX; l >= 0; l--) {
+                const int here = s_longer[l];
+                s_longer[l] = running;
+                running += here;
+            }
+        }
+        __syncthreads();
+        int position = s_longer[key] + __popc(same & ((1u << lane_id) - 1u));
+        for (int w = 0; w < warp_id; w++) position += s_hist[w][key];
+        if (first_slot + position < nb_stride)
+            nb_order[first_slot + position] = static_cast<unsigned char>(t);
+        __syncthreads();  // the next chunk reuses every shared array
     }
 }
 
 #ifndef YB_INTERACT_CTAS
-#define YB_INTERACT_CTAS 8
+#define YB_INTERACT_CTAS 6
 #endif
+#ifndef YB_INTERACT_BALANCE  // walk the cells of a chunk by descending list length
+#define YB_INTERACT_BALANCE 1
+#endif
+#ifndef YB_INTERACT_PREFETCH  // gather partner e + 1 while pair e is evaluated
+#define YB_INTERACT_PREFETCH 1
+#endif
+
+template<typename Pt>
+struct Partner {  // one listed neighbour, as gathered from the cube-ordered planes
+    float4 pos;
+    float4 aux[Layout<Pt>::aux_vec4];
+};
+
+template<typename Pt>
+__device__ __forceinline__ Partner<Pt> gather_partner(
+    const float4* __restrict__ pos4, const float4* __restrict__ aux, int kj)
+{
+    using L = Layout<Pt>;
+    Partner<Pt> p;
+    p.pos = __ldg(pos4 + kj);
+#pragma unroll
+    for (int q = 0; q < L::aux_vec4; q++)
+        p.aux[q] = __ldg(aux + size_t(kj) * L::aux_vec4 + q);
+    return p;
+}
+
+template<typename Pt>
+__device__ __forceinline__ Pt partner_pt(const Partner<Pt>& p)
+{
+    using L = Layout<Pt>;
+    Pt X;
+    lane(X, 0) = p.pos.x, lane(X, 1) = p.pos.y, lane(X, 2) = p.pos.z;
+    const float* a = reinterpret_cast<const float*>(p.aux);
+#pragma unroll
+    for (int e = 0; e < L::extras; e++) lane(X, 3 + e) = a[e];
+    return X;
+}
+
+template<typename Pt>
+__device__ __forceinline__ float3 partner_velocity(const Partner<Pt>& p)
+{
+    const float* a = reinterpret_cast<const float*>(p.aux);
+    constexpr int v = Layout<Pt>::v_lane;
+    return float3{a[v], a[v + 1], a[v + 2]};
+}
 
 template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
     float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
 __global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_lists(
     const int* __restrict__ d_n, int n_max, const float4* __restrict__ pos4,
     const float4* __restrict__ aux, const int* __restrict__ nb,
-    const int* __restrict__ nb_count, int nb_stride, float cube_size, Pt* d_dX,
-    float* __restrict__ partials, int stage, int drift_mode, int fix_point,
-    Step_ctl* ctl)
+    const int* __restrict__ nb_count, const unsigned char* __restrict__ nb_order,
+    int nb_stride, float cube_size, Pt* d_dX, float* __restrict__ partials,
+    int stage, int drift_mode, int fix_point, Step_ctl* ctl)
 {
     using L = Layout<Pt>;
     __shared__ float s_red[3][SWEEP_THREADS / 32];
@@ -777,8 +858,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_list
     float3 my_sum{0.f, 0.f, 0.f};  // this thread's cells, chunk after chunk
 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const int k = chunk * SWEEP_THREADS + t;
-        if (k >= n) continue;
+        const int first_slot = chunk * SWEEP_THREADS;
+        // thread t takes the cell with the t-th longest list of the chunk
+        const int k = first_slot +
+                      (YB_INTERACT_BALANCE ? __ldg(nb_order + first_slot + t) : t);
+        if (first_slot + t >= n || k >= n) continue;
         const float4 me = __ldg(pos4 + k);
         const int my_id = __float_as_int(me.w);
         if (my_id >= n_owned) continue;  // ghost: a partner, never a subject
@@ -788,22 +872,32 @@ __global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_list
         float3 sum_v{0.f, 0.f, 0.f};
         float sum_friction = 0.f;
 
+        // Two gathers deep: while pair e is with the functor, the planes of
+        // partner e + 1 and the list entry e + 2 are already on their way.
         const int* my_nb = nb + k;
+        int kj_next = count > 1 ? __ldg(my_nb + nb_stride) : 0;
+        Partner<Pt> next = gather_partner<Pt>(pos4, aux, count > 0 ? __ldg(my_nb) : k);
         for (int e = 0; e < count; e++) {
-            const int kj = __ldg(my_nb + size_t(e) * nb_stride);
-            const float4* aux_j = aux + size_t(kj) * L::aux_vec4;
-            const float3 vj = velocity_of<Pt>(aux_j);
-            const float4 pj = __ldg(pos4 + kj);
-            const Pt Xj = assemble_pt<Pt>(pj, aux_j);
-            const Pt rij = Xi - Xj;
+#if YB_INTERACT_PREFETCH
+            const Partner<Pt> now = next;
+            const int kj_after =
+                e + 2 < count ? __ldg(my_nb + size_t(e + 2) * nb_stride) : 0;
+            if (e + 1 < count) next = gather_partner<Pt>(pos4, aux, kj_next);
+            kj_next = kj_after;
+#else
+            const Partner<Pt> now = gather_partner<Pt>(
+                pos4, aux, __ldg(my_nb + size_t(e) * nb_stride));
+#endif
+
+            const Pt rij = Xi - partner_pt<Pt>(now);
             const float dist = norm3df(rij.x, rij.y, rij.z);
             if (dist >= cube_size) continue;
 
-            const int j_id = __float_as_int(pj.w);
+            const int j_id = __float_as_int(now.pos.w);
             F += pw_int(Xi, rij, dist, my_id, j_id);
             const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
             sum_friction += friction;
-            if (friction != 0.f) sum_v += friction * vj;
+            if (friction != 0.f) sum_v += friction * partner_velocity<Pt>(now);
         }
 
         Pt dX = F;
@@ -821,7 +915,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_list
     }
 
     // one deterministic CTA-wide sum at the end (chunks are dealt in a fixed
-    // order, so every thread's running sum is reproducible)
+    // order and the cell order inside a chunk is a stable sort, so every
+    // thread's running sum is reproducible)
     __syncthreads();
     const float3 cta_sum =
         block_sum3<SWEEP_THREADS>(my_sum.x, my_sum.y, my_sum.z, s_red);

@@ -45,6 +45,7 @@
 #include "b200/layout.cuh"
 #include "b200/pair_sweep.cuh"
 #include "b200/slab.cuh"
+#include "b200/domain.cuh"
 
 #define YALLA_B200 1
 
@@ -310,6 +311,7 @@ public:
         cudaStreamSynchronize(stream);
         for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
         if (slab.capacity > 0) slab.release();
+        dom.release();
         cudaFreeHost(h_n_pinned);
         cudaEventDestroy(count_ready);
         cudaStreamDestroy(capture_stream);
@@ -402,7 +404,7 @@ public:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0)
             yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
-                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{}, nullptr, nullptr, nullptr);
         else
             yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
@@ -480,7 +482,7 @@ public:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (stage == 0)
             yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n, n_max,
-                dt, d_X, d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
+                dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{}, nullptr, nullptr, nullptr);
         else
             yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
@@ -499,6 +501,106 @@ public:
         if (problems) *problems = snapshot.out_of_grid;
     }
 
+    // ---- Extension: brick decomposition over peer memory ----------------------
+    // One solver per brick and GPU; halo exchange, migration and the global
+    // drift sum are done by kernels that store into the neighbours' memory
+    // (b200/domain.cuh). dom_begin lays out this rank's exchange allocation,
+    // the caller maps the neighbours' allocations (CUDA IPC) and connects them,
+    // dom_step then runs whole Heun steps without the host ever waiting.
+    yb::Domain_link dom;
+
+    void dom_begin(int rank, int world, const float lo[3], const float hi[3],
+        float halo, const int peer_ranks27[27], const int capacity27[27])
+    {
+        yb::Dd_region region{};
+        for (int a = 0; a < 3; a++) region.lo[a] = lo[a], region.hi[a] = hi[a];
+        region.halo = halo;
+        dom.begin(rank, world, region, peer_ranks27, capacity27,
+            yb::Layout<Pt>::lanes + 3, n_max);
+        dd_set_counts(0, 0);
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
+    void dom_step(float dt)
+    {
+        assert(dom.active && dom.connected());
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        for (int stage = 0; stage < 2; stage++) {
+            Pt* X_stage = stage == 0 ? d_X : d_X1;
+            Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
+            dom_round(stage, X_stage);
+            yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(
+                d_ctl, X_stage, d_old_v, dom.inboxes(stage), n_max, d_n);
+            cudaEvent_t sweep_start = nullptr, sweep_stop = nullptr;
+            if (profiling) {
+                YB_CUDA(cudaEventCreate(&sweep_start));
+                YB_CUDA(cudaEventCreate(&sweep_stop));
+            }
+            Computer<Pt>::template pwints<pw_int, pw_friction, false>(stream, d_n,
+                X_stage, d_old_v, dX_stage, d_partials, max_sweep_ctas, stage,
+                yb::DRIFT_MEAN, 0, d_ctl, false, sweep_start);
+            if (profiling) {
+                YB_CUDA(cudaEventRecord(sweep_stop, stream));
+                sweep_events.emplace_back(sweep_start, sweep_stop);
+            }
+            const unsigned epoch = ++dom.drift_epoch;
+            yb::dd_allreduce_drift<<<1, yb::DD_MAX_RANKS, 0, stream>>>(d_ctl,
+                stage, dom.mailboxes, dom.my_mailbox(), dom.rank, dom.world,
+                static_cast<int>(epoch & 1u), epoch);
+            if (stage == 0)
+                yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n,
+                    n_max, dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{},
+                    nullptr, nullptr, nullptr);
+            else
+                yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
+                    d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+        }
+        // migration: cells that crossed a face change owner; the others are
+        // re-stored in the cube order of the last force evaluation
+        dom_round(2, d_X);
+        yb::dd_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, dom.n_stay, d_X1,
+            reinterpret_cast<const float3*>(d_dX), dom.inboxes(2), n_max, d_X,
+            d_old_v, dom.new_count);
+        yb::slab_commit_count<<<1, 1, 0, stream>>>(d_ctl, dom.new_count, d_n);
+        YB_CUDA(cudaGetLastError());
+    }
+
+    // Fill this brick with its share of a seeded, jittered FCC ball.
+    void dom_seed_lattice_ball(
+        float radius, float dist_to_nb, float jitter, unsigned long long seed)
+    {
+        assert(dom.active);
+        const float a = dist_to_nb * 1.41421356237f;
+        const int half = static_cast<int>(ceilf(radius / a)) + 1;
+        const long long side = 2 * half + 1;
+        const long long n_sites = 4 * side * side * side;
+        YB_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int), stream));
+        yb::dd_seed_lattice_ball<Pt><<<yb::sm_count() * 16, 256, 0, stream>>>(
+            radius, dist_to_nb, jitter, seed, dom.region, half, n_sites, n_max,
+            d_X, d_old_v, d_n);
+        const int n = get_d_n();
+        assert(n <= n_max);
+        dd_set_counts(n, n);
+    }
+
+private:
+    // one exchange round: what 0 / 1 = halo of X / X1, 2 = migration
+    void dom_round(int what, const Pt* P)
+    {
+        const bool migration = what == 2;
+        const unsigned epoch = ++dom.epoch[what];
+        // X1 and dX are free at the end of a step: scratch for the stayers
+        yb::dd_select<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
+            dom.scan_ctl, P, d_old_v, dom.region, dom.out[what], migration,
+            d_X1, reinterpret_cast<float3*>(d_dX), dom.n_stay, dom.status,
+            dom.n_tiles,
+            migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr,
+            d_n, n_max, epoch);
+        if (dom.region.n_peers > 0)
+            yb::dd_wait<<<1, 32, 0, stream>>>(d_ctl, dom.inboxes(what), epoch);
+    }
+
+public:
     // Extension: time the pairwise sweep kernels with CUDA events on the
     // launching stream (bench.py's roofline needs the dominant kernel's own
     // duration). While enabled, steps are issued directly instead of replayed
@@ -822,7 +924,7 @@ protected:
         const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
     {
         yb::predictor_step<Pt, false><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
-            d_dX, d_X1, d_ctl, 1.f, 1, 0, 1, nullptr, nullptr, nullptr);
+            d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{}, nullptr, nullptr, nullptr);
     }
 
 private:
@@ -952,7 +1054,7 @@ public:
         if (n > 0) {
             const int blocks = yb::stride_grid(n, 256, sms);
             yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n_scratch, n_max, d_X,
-                cube_size, grid_size, grid_size / 2, n_cubes, sort.key,
+                cube_size, yb::Grid_box::cubic(grid_size), sort.key,
                 sort.arrival, sort.count, d_ctl);
             yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
                 sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
@@ -987,8 +1089,8 @@ public:
 
     Grid_computer(int n_max, int grid_size = 50, float cube_size = 1)
         : cube_size{cube_size}, n_max{n_max}, grid_size{grid_size},
-          n_cubes{grid_size * grid_size * grid_size}, z_half{grid_size / 2},
-          active_cubes{grid_size * grid_size * grid_size}
+          n_cubes{grid_size * grid_size * grid_size},
+          box(yb::Grid_box::cubic(grid_size))
     {
         yb::upload_nhood(grid_size);
         sort.allocate(n_max, n_cubes);
@@ -1002,6 +1104,7 @@ public:
             YB_CUDA(cudaMalloc(
                 &nb, size_t(nb_stride) * yb::LIST_MAX * sizeof(int)));
             YB_CUDA(cudaMalloc(&nb_count, size_t(nb_stride) * sizeof(int)));
+            YB_CUDA(cudaMalloc(&nb_order, size_t(nb_stride) + yb::SWEEP_THREADS));
         }
         // scratch of the state-carrying build tail only
         if (carry_state())
@@ -1012,6 +1115,7 @@ public:
     Grid_computer& operator=(const Grid_computer&) = delete;
     ~Grid_computer()
     {
+        cudaFree(nb_order);
         cudaFree(nb_count);
         cudaFree(nb);
         cudaFree(staged);
@@ -1025,7 +1129,9 @@ protected:
     // everything the stage kernels get by value
     yb::Graph_key graph_key() const
     {
-        return yb::Graph_key{cube_size, 0.f, z_half, active_cubes};
+        return yb::Graph_key{
+            cube_size, 0.f, (box.z_half * 1024 + box.y_half) * 1024 + box.x_half,
+            box.n_cubes};
     }
 
     // Resident CTAs per SM of a persistent sweep kernel (queried once).
@@ -1114,17 +1220,15 @@ protected:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         if (!binned_by_predictor)
             yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, cube_size,
-                grid_size, z_half, active_cubes, sort.key, sort.arrival,
-                sort.count, d_ctl);
-        const int tiles = yb::ceil_div(active_cubes + 1, yb::SCAN_TILE);
+                box, sort.key, sort.arrival, sort.count, d_ctl);
+        const int tiles = yb::ceil_div(box.n_cubes + 1, yb::SCAN_TILE);
         yb::scan_bins<<<tiles, yb::SCAN_THREADS, 0, s>>>(
             sort.count, sort.offset, tiles, sort.status, d_ctl);
         if (carry_state()) {
             yb::place_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, d_old_v,
                 sort.key, sort.arrival, sort.offset, staged);
             yb::settle_cells<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, staged,
-                sort.offset, cube_size, grid_size, z_half, active_cubes, pos4,
-                aux, cube_sorted);
+                sort.offset, cube_size, box, pos4, aux, cube_sorted);
         } else {
             yb::place_ids<<<blocks, 256, 0, s>>>(
                 d_n, n_max, sort.key, sort.arrival, sort.offset, sort.slot_id);
@@ -1195,31 +1299,30 @@ protected:
             yb::list_cubes<<<persistent_ctas(prepare_list(), yb::SWEEP_THREADS,
                                  max_ctas),
                 yb::SWEEP_THREADS, yb::List_config::smem, s>>>(d_n, n_max, pos4,
-                cube_sorted, sort.offset, cube_size, grid_size, z_half,
-                active_cubes, nb, nb_count, nb_stride, d_ctl);
+                cube_sorted, sort.offset, cube_size, box, nb, nb_count,
+                nb_order, nb_stride, d_ctl);
             yb::interact_lists<Pt, pw_int, pw_friction, SEEDED>
                 <<<persistent_ctas(
                        prepare_interact<pw_int, pw_friction, SEEDED>(),
                        yb::SWEEP_THREADS, max_ctas),
                     yb::SWEEP_THREADS, 0, s>>>(d_n, n_max, pos4, aux, nb,
-                    nb_count, nb_stride, cube_size, d_dX, d_partials, stage,
-                    drift_mode, fix_point, d_ctl);
+                    nb_count, nb_order, nb_stride, cube_size, d_dX, d_partials,
+                    stage, drift_mode, fix_point, d_ctl);
         }
         // alone, or as the fallback for crowded tissues behind the pair above
         yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>
             <<<ctas, yb::SWEEP_THREADS,
                 yb::Sweep_config<yb::Layout<Pt>::lanes>::smem, s>>>(d_n, n_max, pos4,
-                aux, cube_sorted, sort.offset, cube_size, grid_size, z_half,
-                active_cubes, d_dX, d_partials, stage, drift_mode, fix_point,
-                d_ctl, split ? 1 : 0);
+                aux, cube_sorted, sort.offset, cube_size, box, d_dX, d_partials,
+                stage, drift_mode, fix_point, d_ctl, split ? 1 : 0);
     }
 
     void predict(cudaStream_t s, int blocks, const int* d_n, float dt,
         const Pt* d_X, const Pt* d_dX, Pt* d_X1, yb::Step_ctl* d_ctl)
     {
         yb::predictor_step<Pt, true><<<blocks, 256, 0, s>>>(d_n, n_max, dt, d_X,
-            d_dX, d_X1, d_ctl, cube_size, grid_size, z_half, active_cubes,
-            sort.key, sort.arrival, sort.count);
+            d_dX, d_X1, d_ctl, cube_size, box, sort.key, sort.arrival,
+            sort.count);
     }
 
     yb::Bucket_sort sort;
@@ -1229,21 +1332,35 @@ protected:
     float4* staged = nullptr;  // cube order, arrival order inside cubes (place_cells)
     int* nb = nullptr;         // neighbour lists of the split sweep, entry-major
     int* nb_count = nullptr;
+    unsigned char* nb_order = nullptr;  // per chunk: cells by descending count
     int nb_stride = 0;
     const int n_max, grid_size, n_cubes;
-    // z numbering of the grid: the reference's cubic grid by default; a slab of
-    // a decomposed domain uses only its own layers (dd_slab_grid below)
-    int z_half, active_cubes;
+    // the cubes the solver works on: the reference's cubic grid by default; a
+    // domain of a decomposed tissue only its own box (dd_box_grid below)
+    yb::Grid_box box;
 
 public:
-    // Extension (domain decomposition): restrict the grid to the z layers
-    // [first_layer, first_layer + n_layers) of the global cubic grid. Keeps the
-    // per-cube tables (and the scan over them) proportional to the slab.
+    // Extension (domain decomposition): restrict the grid to the box of
+    // n[0] x n[1] x n[2] cubes starting at cube first[] of the global cubic
+    // grid. Keeps the per-cube tables (and the scan over them) proportional
+    // to the domain. The box must fit the tables allocated for grid_size^3.
+    void dd_box_grid(const int first[3], const int n[3])
+    {
+        const long long cubes = 1LL * n[0] * n[1] * n[2];
+        assert(n[0] >= 1 && n[1] >= 1 && n[2] >= 1 && cubes <= n_cubes);
+        box.nx = n[0], box.ny = n[1], box.nz = n[2];
+        box.x_half = grid_size / 2 - first[0];
+        box.y_half = grid_size / 2 - first[1];
+        box.z_half = grid_size / 2 - first[2];
+        box.n_cubes = static_cast<int>(cubes);
+        box.restricted = 1;
+    }
+    // z layers [first_layer, first_layer + n_layers) of the cubic grid
     void dd_slab_grid(int first_layer, int n_layers)
     {
-        assert(n_layers >= 1 && n_layers <= grid_size);
-        z_half = grid_size / 2 - first_layer;
-        active_cubes = grid_size * grid_size * n_layers;
+        const int first[3] = {0, 0, first_layer};
+        const int n[3] = {grid_size, grid_size, n_layers};
+        dd_box_grid(first, n);
     }
 };
 

@@ -201,6 +201,52 @@ int yb_slab_unpack(yb_sim* sim, int what, const float* recv_lo,
 int yb_slab_update(yb_sim* sim, int stage, float dt, const float* sums4);
 int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems);
 
+/* ---- brick decomposition over peer memory (product library only) ---------------
+ * The tissue is cut into bricks, one model instance per brick and GPU; the
+ * halo exchange, the migration of cells and the global drift sum are done by
+ * the library's kernels storing straight into the neighbours' memory over
+ * NVLink (include/b200/domain.cuh) -- yb_dom_step never waits for the host and
+ * calls no communication library. Set-up, once:
+ *
+ *  yb_dom_begin     this instance is rank `rank` of `world`; it owns
+ *                   lo3 <= (x, y, z) < hi3 (+-INFINITY at the tissue's ends) and
+ *                   copies cells within `halo` of a face to the neighbour
+ *                   behind it. peer_ranks27[d] is the rank of the neighbour in
+ *                   direction d = (dx + 1) + 3 (dy + 1) + 9 (dz + 1), or -1;
+ *                   capacity27[d] the records its inbox for that neighbour
+ *                   holds. box_first3 / box_n3: the cubes of the global grid
+ *                   this brick can touch (box_n3[0] <= 0: the whole grid).
+ *  yb_dom_exchange  device address and size of this rank's exchange allocation
+ *                   and, per direction d, the byte offsets of its three
+ *                   inboxes and three flag words (offsets27x6_out[6 d + q],
+ *                   -1 without a neighbour). Other processes map the
+ *                   allocation with yb_ipc_export / yb_ipc_import.
+ *  yb_dom_connect   the neighbour in `direction` keeps this rank's records at
+ *                   d_peer_base (its allocation as mapped here) + the offsets
+ *                   IT reported for the opposite direction, 26 - direction.
+ *  yb_dom_connect_mailbox   every rank's allocation (its mailbox is at offset
+ *                   0), this rank's own included, for the drift sum.
+ *
+ * yb_dom_seed_lattice_ball fills the brick with its share of a jittered FCC
+ * ball generated on the device (same tissue however it is cut);
+ * yb_slab_set_owned / yb_dd_read / yb_slab_counts load, read and count cells. */
+int yb_dom_begin(yb_sim* sim, int rank, int world, const float* lo3,
+    const float* hi3, float halo, const int* peer_ranks27,
+    const int* capacity27, const int* box_first3, const int* box_n3);
+int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,
+    long long* offsets27x6_out);
+int yb_dom_connect(yb_sim* sim, int direction, void* d_peer_base,
+    const long long* peer_offsets6);
+int yb_dom_connect_mailbox(yb_sim* sim, int rank, void* d_peer_base);
+int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
+    float jitter, unsigned long long seed, int* n_out);
+int yb_dom_step(yb_sim* sim, float dt, int n_steps);
+/* CUDA IPC plumbing for the above: 64-byte handle of a device allocation,
+ * mapping of another process's handle, unmapping. */
+int yb_ipc_export(const void* d_base, unsigned char* handle64);
+int yb_ipc_import(const unsigned char* handle64, void** d_base_out);
+int yb_ipc_release(void* d_base);
+
 /* Current cell count (blocking read of d_n: Solution::get_d_n). */
 int yb_sim_n(yb_sim* sim, int* n_out);
 int yb_sim_sync(yb_sim* sim);

@@ -1040,6 +1040,43 @@ int yb_sim_step_host_async(
 {
     return fail(YB_ENOSYS, "asynchronous steps need the product library");
 }
+int yb_dom_begin(yb_sim*, int, int, const float*, const float*, float,
+    const int*, const int*, const int*, const int*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_dom_exchange(yb_sim*, void**, long long*, long long*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_dom_connect(yb_sim*, int, void*, const long long*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_dom_connect_mailbox(yb_sim*, int, void*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_dom_seed_lattice_ball(yb_sim*, float, float, float, unsigned long long, int*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_dom_step(yb_sim*, float, int)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_ipc_export(const void*, unsigned char*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_ipc_import(const unsigned char*, void**)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
+int yb_ipc_release(void*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
 int yb_sim_host_drain(yb_sim*)
 {
     return fail(YB_ENOSYS, "asynchronous steps need the product library");

@@ -1,0 +1,144 @@
+"""Brick decomposition over peer memory (include/b200/domain.cuh, dd.BrickDomain).
+
+GPU (-m gpu): 2, 3 and 4 bricks of one tissue live in ONE process on one device,
+each on its own stream, connected through plain device pointers -- the very
+kernels, flags and epochs that run across GPUs over CUDA IPC
+(scripts/dd_bricks_check.py under torchrun) -- and must reproduce the
+single-domain run of the same library. CPU: the host-side layout logic.
+"""
+import numpy as np
+import pytest
+
+from yalla_b200 import dd, workloads
+
+
+# ---- host logic (CPU) ----------------------------------------------------------
+def test_brick_grids_and_ranks():
+    assert dd.brick_grid_for(1) == (1, 1, 1)
+    assert dd.brick_grid_for(2) == (1, 1, 2)
+    assert dd.brick_grid_for(4) == (1, 2, 2)
+    assert dd.brick_grid_for(8) == (2, 2, 2)
+    assert dd.brick_grid_for(6) == (1, 2, 3)
+    for world in (2, 4, 8, 12):
+        bricks = dd.brick_grid_for(world)
+        seen = set()
+        for rank in range(world):
+            coord = dd.brick_coord(rank, bricks)
+            assert dd.brick_rank(coord, bricks) == rank
+            seen.add(coord)
+        assert len(seen) == world
+
+
+def test_ball_brick_cuts_are_on_cube_boundaries_and_balanced():
+    radius = 40.0
+    cuts = dd.ball_brick_cuts(radius, (2, 2, 2))
+    assert cuts == [[0.0], [0.0], [0.0]]
+    cuts = dd.ball_brick_cuts(radius, (1, 1, 4))
+    assert cuts[0] == [] and cuts[1] == [] and len(cuts[2]) == 3
+    assert all(float(c).is_integer() for c in cuts[2])
+    rng = np.random.default_rng(0)
+    X = workloads.random_ball(200_000, 0.8, rng) * (radius / workloads.ball_radius(
+        200_000, 0.8))
+    share = np.histogram(X[:, 2], bins=[-np.inf] + cuts[2] + [np.inf])[0] / len(X)
+    assert np.all(np.abs(share - 0.25) < 0.03)
+
+
+# ---- the decomposed run on one GPU ------------------------------------------------
+def match_cells(got, want, tol):
+    from scipy.spatial import cKDTree
+    assert got.shape == want.shape
+    distance, index = cKDTree(want[:, :3]).query(got[:, :3], k=1)
+    assert len(np.unique(index)) == len(want), "cells lost or duplicated"
+    assert distance.max() < tol, f"max deviation {distance.max():.3e}"
+    return float(np.max(np.abs(got - want[index])))
+
+
+def run_bricks(product, model, X, bricks, steps, dt, gs):
+    import torch
+    world = bricks[0] * bricks[1] * bricks[2]
+    radius = float(np.max(np.linalg.norm(X[:, :3], axis=1)))
+    cuts = dd.ball_brick_cuts(radius, bricks)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    domains = [dd.BrickDomain(product, model, len(X), gs, 1.0, bricks, cuts, rank,
+                              world, face_capacity=len(X))
+               for rank in range(world)]
+    for domain, stream in zip(domains, streams):
+        domain.sim.set_stream(stream.cuda_stream)
+    dd.connect_local(domains)
+    before = []
+    for domain in domains:
+        mine = X[domain.owns(X)]
+        before.append(len(mine))
+        domain.set_cells(mine)
+    for _ in range(steps):
+        for domain in domains:
+            domain.step(dt)
+    torch.cuda.synchronize()
+    parts, ghosts, after = [], 0, []
+    for domain in domains:
+        owned, with_ghosts, problems = domain.counts()
+        assert problems == 0
+        ghosts += with_ghosts - owned
+        after.append(owned)
+        parts.append(domain.owned_state()[0].cpu().numpy())
+    for domain in domains:
+        domain.close()
+    return np.concatenate(parts), ghosts, before, after
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,lanes,bricks", [
+    ("relu_grid", 3, (1, 1, 2)), ("relu_grid", 3, (1, 1, 3)),
+    ("relu_grid", 3, (1, 2, 2)), ("epithelium", 5, (1, 2, 2)),
+    ("relu_grid", 3, (2, 2, 1))])
+def test_bricks_match_single_domain(product, model, lanes, bricks):
+    rng = np.random.default_rng(41)
+    n, steps = 30_000, 6
+    dt = 0.1 if lanes == 3 else 0.05
+    if lanes == 3:
+        # squeezed lattice: the tissue expands, cells cross the cuts
+        X = workloads.lattice_ball(n, 0.8, rng) * 0.9
+    else:
+        X = workloads.polarized_ball(n, 0.8, rng, lattice=True)
+        X[:, :3] *= 0.9
+    X = X.astype(np.float32)
+    gs = workloads.grid_size_for(n, 0.8) + 4
+    with product.sim(model, n, gs, 1.0) as sim:
+        sim.set_state(X)
+        sim.step(dt, steps)
+        want = sim.get_state()
+    got, ghosts, before, after = run_bricks(product, model, X, bricks, steps, dt, gs)
+    assert len(got) == n and ghosts > 0
+    assert before != after, "no cell migrated: the test is too tame"
+    error = match_cells(got, want, 1e-3)
+    assert error < 2e-5 * steps * max(float(np.max(np.abs(want))), 1.0)
+
+
+@pytest.mark.gpu
+def test_seeded_lattice_ball_is_the_same_tissue_however_it_is_cut(product):
+    import torch
+    radius, d = 20.0, 0.8
+    gs = int(2 * radius) + 8
+    tissues = []
+    for bricks in ((1, 1, 1), (1, 2, 2)):
+        world = bricks[0] * bricks[1] * bricks[2]
+        cuts = dd.ball_brick_cuts(radius, bricks)
+        domains = [dd.BrickDomain(product, "relu_grid", 60_000, gs, 1.0, bricks, cuts,
+                                  rank, world, face_capacity=60_000)
+                   for rank in range(world)]
+        streams = [torch.cuda.Stream() for _ in domains]
+        for domain, stream in zip(domains, streams):
+            domain.sim.set_stream(stream.cuda_stream)
+        dd.connect_local(domains)
+        counts = [domain.seed_lattice_ball(radius, d, seed=7) for domain in domains]
+        cells = np.concatenate([domain.owned_state()[0].cpu().numpy()
+                                for domain in domains])
+        assert sum(counts) == len(cells)
+        for domain in domains:
+            domain.close()
+        tissues.append(cells[np.lexsort(cells.T[::-1])])
+    assert tissues[0].shape == tissues[1].shape
+    assert np.array_equal(tissues[0], tissues[1])
+    # density of an FCC lattice with nearest-neighbour distance d
+    expected = np.sqrt(2.0) / d ** 3 * 4.0 / 3.0 * np.pi * radius ** 3
+    assert abs(len(tissues[0]) - expected) < 0.02 * expected

@@ -91,6 +91,27 @@ SIGNATURES = {
                                       ctypes.c_float, ctypes.c_void_p]),
     "yb_slab_counts": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_int_p,
                                       _c_int_p]),
+    "yb_dom_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_float, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
+    "yb_dom_exchange": (ctypes.c_int, [ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(ctypes.c_longlong),
+                                       ctypes.c_void_p]),
+    "yb_dom_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_dom_connect_mailbox": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_void_p]),
+    "yb_dom_seed_lattice_ball": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_ulonglong, _c_int_p]),
+    "yb_dom_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_int]),
+    "yb_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_ipc_import": (ctypes.c_int, [ctypes.c_void_p,
+                                     ctypes.POINTER(ctypes.c_void_p)]),
+    "yb_ipc_release": (ctypes.c_int, [ctypes.c_void_p]),
     "yb_sim_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "yb_sim_step_host_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int, ctypes.c_float,
@@ -175,6 +196,21 @@ class Library:
         self.check(self.cdll.yb_grid_build(
             d_X, lanes, n, grid_size, cube_size, d_cube_id, d_point_id,
             d_cube_start, d_cube_end), "yb_grid_build")
+
+    def ipc_export(self, d_base):
+        handle = (ctypes.c_ubyte * 64)()
+        self.check(self.cdll.yb_ipc_export(d_base, handle), "yb_ipc_export")
+        return bytes(handle)
+
+    def ipc_import(self, handle_bytes):
+        handle = (ctypes.c_ubyte * 64).from_buffer_copy(handle_bytes)
+        base = ctypes.c_void_p()
+        self.check(self.cdll.yb_ipc_import(handle, ctypes.byref(base)),
+                   "yb_ipc_import")
+        return base.value
+
+    def ipc_release(self, d_base):
+        self.check(self.cdll.yb_ipc_release(d_base), "yb_ipc_release")
 
     def link_forces(self, d_X, d_dX, lanes, n, d_links, n_links, strength):
         self.check(self.cdll.yb_link_forces(
@@ -347,6 +383,47 @@ class Sim:
             self.handle, ctypes.byref(owned), ctypes.byref(total),
             ctypes.byref(problems)), "slab_counts")
         return owned.value, total.value, problems.value
+
+    # ---- brick decomposition over peer memory ----------------------------------
+    def dom_begin(self, rank, world, lo, hi, halo, peer_ranks27, capacity27,
+                  box_first=(0, 0, 0), box_n=(0, 0, 0)):
+        lo, hi = _f32(lo), _f32(hi)
+        peers, caps = _i32(peer_ranks27), _i32(capacity27)
+        first, count = _i32(box_first), _i32(box_n)
+        self.lib.check(self.lib.cdll.yb_dom_begin(
+            self.handle, rank, world, lo.ctypes.data, hi.ctypes.data, halo,
+            peers.ctypes.data, caps.ctypes.data, first.ctypes.data,
+            count.ctypes.data), "dom_begin")
+
+    def dom_exchange(self):
+        """-> (device address, bytes, offsets[27, 6]) of this rank's exchange
+        allocation: per direction the offsets of 3 inboxes and 3 flag words."""
+        base, size = ctypes.c_void_p(), ctypes.c_longlong()
+        offsets = np.zeros((27, 6), dtype=np.int64)
+        self.lib.check(self.lib.cdll.yb_dom_exchange(
+            self.handle, ctypes.byref(base), ctypes.byref(size),
+            offsets.ctypes.data), "dom_exchange")
+        return base.value, size.value, offsets
+
+    def dom_connect(self, direction, peer_base, peer_offsets6):
+        offsets = np.ascontiguousarray(peer_offsets6, dtype=np.int64)
+        self.lib.check(self.lib.cdll.yb_dom_connect(
+            self.handle, direction, peer_base, offsets.ctypes.data), "dom_connect")
+
+    def dom_connect_mailbox(self, rank, peer_base):
+        self.lib.check(self.lib.cdll.yb_dom_connect_mailbox(
+            self.handle, rank, peer_base), "dom_connect_mailbox")
+
+    def dom_seed_lattice_ball(self, radius, dist_to_nb, jitter, seed):
+        n = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_dom_seed_lattice_ball(
+            self.handle, radius, dist_to_nb, jitter, seed, ctypes.byref(n)),
+            "dom_seed_lattice_ball")
+        return n.value
+
+    def dom_step(self, dt, n_steps=1):
+        self.lib.check(self.lib.cdll.yb_dom_step(self.handle, dt, n_steps),
+                       "dom_step")
 
     def profile_sweeps(self, enable=True):
         self.lib.check(self.lib.cdll.yb_sim_profile_sweeps(

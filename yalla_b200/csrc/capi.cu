@@ -137,6 +137,31 @@ struct yb_sim {
     {
         return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
     }
+    virtual int dom_begin(int, int, const float*, const float*, float, const int*,
+        const int*, const int*, const int*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dom_exchange(void**, long long*, long long*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dom_connect(int, void*, const long long*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dom_connect_mailbox(int, void*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dom_seed_lattice_ball(float, float, float, unsigned long long, int*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
+    virtual int dom_step(float, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
     virtual int profile_sweeps(int enable)
     {
         return fail(YB_ENOSYS, "sweep profiling needs the product library");
@@ -457,6 +482,87 @@ struct Sim_base : yb_sim {
         cells.slab_counts(n_owned, n_total, problems);
         return check_cuda("yb_slab_counts");
     }
+    // ---- brick decomposition over peer memory (b200/domain.cuh) ---------------
+    int dom_begin(int rank, int world, const float* lo3, const float* hi3,
+        float halo, const int* peer_ranks27, const int* capacity27,
+        const int* box_first3, const int* box_n3) override
+    {
+        return dom_begin_impl(rank, world, lo3, hi3, halo, peer_ranks27,
+            capacity27, box_first3, box_n3,
+            std::is_same<Solver<Pt>, Grid_solver<Pt>>{});
+    }
+    int dom_begin_impl(int rank, int world, const float* lo3, const float* hi3,
+        float halo, const int* peer_ranks27, const int* capacity27,
+        const int* box_first3, const int* box_n3, std::true_type)
+    {
+        if (world < 1 || world > yb::DD_MAX_RANKS || rank < 0 || rank >= world)
+            return fail(YB_EINVAL, "bad rank / world");
+        for (int d = 0; d < 27; d++)
+            if (d != 13 && peer_ranks27[d] >= 0 && capacity27[d] <= 0)
+                return fail(YB_EINVAL, "a neighbour needs a positive capacity");
+        if (box_n3 != nullptr && box_n3[0] > 0)
+            cells.dd_box_grid(box_first3, box_n3);
+        cells.dom_begin(rank, world, lo3, hi3, halo, peer_ranks27, capacity27);
+        return check_cuda("yb_dom_begin");
+    }
+    int dom_begin_impl(int, int, const float*, const float*, float, const int*,
+        const int*, const int*, const int*, std::false_type)
+    {
+        return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
+    }
+    int dom_exchange(void** base, long long* bytes, long long* offsets) override
+    {
+        const yb::Domain_link& dom = cells.dom;
+        if (!dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
+        *base = dom.base;
+        *bytes = static_cast<long long>(dom.bytes);
+        for (int q = 0; q < 27 * 6; q++) offsets[q] = -1;
+        for (int p = 0; p < dom.region.n_peers; p++)
+            for (int q = 0; q < yb::DD_ROUNDS; q++) {
+                offsets[dom.peer_direction[p] * 6 + q] =
+                    static_cast<long long>(dom.inbox_offset[p][q]);
+                offsets[dom.peer_direction[p] * 6 + 3 + q] =
+                    static_cast<long long>(dom.flag_offset[p][q]);
+            }
+        return YB_OK;
+    }
+    int dom_connect(int direction, void* peer_base,
+        const long long* peer_offsets6) override
+    {
+        if (!cells.dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
+        for (int q = 0; q < 6; q++)
+            if (peer_offsets6[q] < 0)
+                return fail(YB_EINVAL, "the peer has no inbox for this direction");
+        if (!cells.dom.connect(direction, peer_base, peer_offsets6))
+            return fail(YB_EINVAL, "no neighbour in this direction");
+        return YB_OK;
+    }
+    int dom_connect_mailbox(int rank, void* peer_base) override
+    {
+        if (!cells.dom.active || rank < 0 || rank >= cells.dom.world)
+            return fail(YB_EINVAL, "bad rank");
+        cells.dom.connect_mailbox(rank, peer_base);
+        return YB_OK;
+    }
+    int dom_seed_lattice_ball(float radius, float dist_to_nb, float jitter,
+        unsigned long long seed, int* n_out) override
+    {
+        if (!cells.dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
+        cells.dom_seed_lattice_ball(radius, dist_to_nb, jitter, seed);
+        int problems = 0;
+        cells.slab_counts(n_out, nullptr, &problems);
+        return check_cuda("yb_dom_seed_lattice_ball");
+    }
+    template<Pairwise_interaction<Pt> force, Pairwise_friction<Pt> friction>
+    int dom_step_with(float dt, int n_steps)
+    {
+        if (!cells.dom.active || !cells.dom.connected())
+            return fail(YB_EINVAL, "the domain is not connected to its neighbours");
+        for (int k = 0; k < n_steps; k++)
+            cells.template dom_step<force, friction>(dt);
+        return check_cuda("yb_dom_step");
+    }
+
     // the sweep needs the model's functor: models that support decomposition
     // call this from their dd_forces override
     template<Pairwise_interaction<Pt> force, Pairwise_friction<Pt> friction>
@@ -554,6 +660,14 @@ struct Spring_sim : Sim_base<float3, Solver> {
         else
             return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
     }
+    int dom_step(float dt, int n_steps) override
+    {
+        if constexpr (std::is_same<Solver<float3>, Grid_solver<float3>>::value)
+            return Base::template dom_step_with<force,
+                friction_w_neighbour<float3>>(dt, n_steps);
+        else
+            return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
+    }
 #endif
 };
 
@@ -620,6 +734,11 @@ struct Epithelium_sim : Sim_base<Po_cell, Grid_solver> {
     {
         return dd_forces_with<models::layer_force, friction_on_background<Po_cell>>(
             stage, sums4);
+    }
+    int dom_step(float dt, int n_steps) override
+    {
+        return dom_step_with<models::layer_force, friction_on_background<Po_cell>>(
+            dt, n_steps);
     }
 #endif
 };
@@ -1202,6 +1321,68 @@ int yb_slab_update(yb_sim* sim, int stage, float dt, const float* sums4)
 int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems)
 {
     return sim->slab_counts(n_owned, n_total, problems);
+}
+
+int yb_dom_begin(yb_sim* sim, int rank, int world, const float* lo3,
+    const float* hi3, float halo, const int* peer_ranks27,
+    const int* capacity27, const int* box_first3, const int* box_n3)
+{
+    return sim->dom_begin(rank, world, lo3, hi3, halo, peer_ranks27, capacity27,
+        box_first3, box_n3);
+}
+
+int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,
+    long long* offsets27x6_out)
+{
+    return sim->dom_exchange(d_base_out, bytes_out, offsets27x6_out);
+}
+
+int yb_dom_connect(yb_sim* sim, int direction, void* d_peer_base,
+    const long long* peer_offsets6)
+{
+    return sim->dom_connect(direction, d_peer_base, peer_offsets6);
+}
+
+int yb_dom_connect_mailbox(yb_sim* sim, int rank, void* d_peer_base)
+{
+    return sim->dom_connect_mailbox(rank, d_peer_base);
+}
+
+int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
+    float jitter, unsigned long long seed, int* n_out)
+{
+    return sim->dom_seed_lattice_ball(radius, dist_to_nb, jitter, seed, n_out);
+}
+
+int yb_dom_step(yb_sim* sim, float dt, int n_steps)
+{
+    return sim->dom_step(dt, n_steps);
+}
+
+int yb_ipc_export(const void* d_base, unsigned char* handle64)
+{
+    cudaIpcMemHandle_t handle;
+    static_assert(sizeof(handle) == 64, "CUDA IPC handles are 64 bytes");
+    if (cudaIpcGetMemHandle(&handle, const_cast<void*>(d_base)) != cudaSuccess)
+        return check_cuda("yb_ipc_export");
+    memcpy(handle64, &handle, sizeof(handle));
+    return YB_OK;
+}
+
+int yb_ipc_import(const unsigned char* handle64, void** d_base_out)
+{
+    cudaIpcMemHandle_t handle;
+    memcpy(&handle, handle64, sizeof(handle));
+    if (cudaIpcOpenMemHandle(d_base_out, handle, cudaIpcMemLazyEnablePeerAccess) !=
+        cudaSuccess)
+        return check_cuda("yb_ipc_import");
+    return YB_OK;
+}
+
+int yb_ipc_release(void* d_base)
+{
+    cudaIpcCloseMemHandle(d_base);
+    return check_cuda("yb_ipc_release");
 }
 
 int yb_sim_profile_sweeps(yb_sim* sim, int enable)

@@ -207,3 +207,170 @@ class SlabDomain:
         dist.all_gather_into_tensor(parts, mine, group=self.group)
         parts = parts.view(self.world, pad, self.lanes)
         return torch.cat([parts[r, :every[r]] for r in range(self.world)]).cpu().numpy()
+
+
+# ---- brick decomposition over peer memory (include/b200/domain.cuh) -----------
+def brick_grid_for(world):
+    """(bx, by, bz) bricks for `world` GPUs: slabs for 2, 2 x 2 x 1 for 4,
+    2 x 2 x 2 for 8; otherwise the most cubic factorisation."""
+    best = None
+    for bz in range(1, world + 1):
+        if world % bz:
+            continue
+        for by in range(1, world // bz + 1):
+            if (world // bz) % by:
+                continue
+            bx = world // (bz * by)
+            if bx <= by <= bz:
+                shape = (bx, by, bz)
+                if best is None or max(shape) < max(best):
+                    best = shape
+    return best
+
+
+def brick_coord(rank, bricks):
+    bx, by, _ = bricks
+    return rank % bx, (rank // bx) % by, rank // (bx * by)
+
+
+def brick_rank(coord, bricks):
+    return coord[0] + bricks[0] * (coord[1] + bricks[1] * coord[2])
+
+
+def ball_brick_cuts(radius, bricks, cube_size=1.0):
+    """Per axis, the cut positions that split a ball into equal-volume slabs
+    along that axis (the bricks are their tensor product)."""
+    return [ball_slab_cuts(radius, n, cube_size) for n in bricks]
+
+
+class BrickDomain:
+    """One rank's brick. Set-up is host work (layout, CUDA IPC handles gathered
+    with torch.distributed or plain pointers inside one process); after
+    connect() a step is one call into the library, which posts kernels only:
+    halo exchange, migration and the drift sum are stores into the neighbours'
+    memory over NVLink, ordered by flags the kernels themselves wait on."""
+
+    def __init__(self, lib, model, n_max, grid_size, cube_size, bricks, cuts,
+                 rank, world, face_capacity, halo=1.5, local_grid=True):
+        assert world == bricks[0] * bricks[1] * bricks[2]
+        self.lib = lib
+        self.sim = lib.sim(model, n_max, grid_size, cube_size)
+        self.lanes = self.sim.lanes
+        self.n_max = n_max
+        self.rank, self.world = rank, world
+        self.bricks = tuple(bricks)
+        self.coord = brick_coord(rank, bricks)
+        self.halo = halo * cube_size
+        bounds = [[-np.inf] + list(cuts[a]) + [np.inf] for a in range(3)]
+        self.lo = np.array([bounds[a][self.coord[a]] for a in range(3)], np.float32)
+        self.hi = np.array([bounds[a][self.coord[a] + 1] for a in range(3)],
+                           np.float32)
+        self.peer_ranks = np.full(27, -1, dtype=np.int32)
+        self.capacity = np.zeros(27, dtype=np.int32)
+        for d in range(27):
+            if d == 13:
+                continue
+            step = (d % 3 - 1, (d // 3) % 3 - 1, d // 9 - 1)
+            there = tuple(self.coord[a] + step[a] for a in range(3))
+            if all(0 <= there[a] < bricks[a] for a in range(3)):
+                self.peer_ranks[d] = brick_rank(there, bricks)
+                axes = sum(1 for s in step if s != 0)  # 1 face, 2 edge, 3 corner
+                self.capacity[d] = (face_capacity if axes == 1 else
+                                    face_capacity // 16 + 2048 if axes == 2 else
+                                    face_capacity // 256 + 2048)
+        # the cubes this brick can touch: its own range plus the halo and two
+        # cubes of slack for cells on the move
+        first, count = [0, 0, 0], [0, 0, 0]
+        if local_grid and world > 1:
+            half = grid_size // 2
+            for a in range(3):
+                lo = -half if not np.isfinite(self.lo[a]) else int(
+                    np.floor((self.lo[a] - self.halo) / cube_size)) - 2
+                hi = half if not np.isfinite(self.hi[a]) else int(
+                    np.ceil((self.hi[a] + self.halo) / cube_size)) + 2
+                lo, hi = max(lo, -half), min(hi, half)
+                first[a], count[a] = lo + half, hi - lo
+        self.sim.dom_begin(rank, world, self.lo, self.hi, self.halo,
+                           self.peer_ranks, self.capacity, first, count)
+        self.mapped = []
+
+    def close(self):
+        self.sim.sync()
+        for base in self.mapped:
+            self.lib.ipc_release(base)
+        self.mapped = []
+        self.sim.close()
+
+    def connect(self, bases, offsets):
+        """bases[r]: rank r's exchange allocation as an address valid in this
+        process; offsets[r]: its [27, 6] table (Sim.dom_exchange)."""
+        for d in range(27):
+            r = int(self.peer_ranks[d])
+            if r >= 0:
+                self.sim.dom_connect(d, bases[r], offsets[r][26 - d])
+        for r in range(self.world):
+            self.sim.dom_connect_mailbox(r, bases[r])
+
+    def connect_over_ipc(self, group=None):
+        """Gather everybody's CUDA IPC handle and offsets (torch.distributed is
+        the plumbing), map the other ranks' allocations, connect."""
+        base, _, offsets = self.sim.dom_exchange()
+        if self.world == 1:
+            return self.connect([base], [offsets])
+        mine = (self.lib.ipc_export(base), offsets)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        bases = []
+        for r, (handle, _) in enumerate(everyone):
+            if r == self.rank:
+                bases.append(base)
+            else:
+                bases.append(self.lib.ipc_import(handle))
+                self.mapped.append(bases[-1])
+        self.connect(bases, [table for _, table in everyone])
+        dist.barrier(group=group)
+
+    # ---- state -------------------------------------------------------------------
+    def owns(self, X):
+        inside = np.ones(len(X), dtype=bool)
+        for a in range(3):
+            inside &= (X[:, a] >= self.lo[a]) & (X[:, a] < self.hi[a])
+        return inside
+
+    def set_cells(self, X, v=None, device="cuda"):
+        X = torch.as_tensor(np.ascontiguousarray(X, np.float32)).reshape(
+            -1, self.lanes).to(device)
+        if v is None:
+            v = torch.zeros((len(X), 3), dtype=torch.float32, device=device)
+        else:
+            v = torch.as_tensor(np.ascontiguousarray(v, np.float32)).to(device)
+        self.sim.slab_set_owned(X.data_ptr(), v.data_ptr(), len(X))
+        torch.cuda.synchronize()
+
+    def seed_lattice_ball(self, radius, dist_to_nb, seed, jitter=0.05):
+        return self.sim.dom_seed_lattice_ball(radius, dist_to_nb, jitter, seed)
+
+    def counts(self):
+        """(owned, owned + ghosts, problems) -- blocks."""
+        return self.sim.slab_counts()
+
+    def owned_state(self, device="cuda"):
+        n = self.counts()[0]
+        X = torch.empty((n, self.lanes), dtype=torch.float32, device=device)
+        v = torch.empty((n, 3), dtype=torch.float32, device=device)
+        self.sim.dd_read(0, X.data_ptr(), n)
+        self.sim.dd_read(2, v.data_ptr(), n)
+        torch.cuda.synchronize()
+        return X, v
+
+    def step(self, dt, n_steps=1):
+        self.sim.dom_step(dt, n_steps)
+
+
+def connect_local(domains):
+    """All bricks live in this process (tests, one GPU): plain device pointers."""
+    info = [d.sim.dom_exchange() for d in domains]
+    bases = [base for base, _, _ in info]
+    offsets = [table for _, _, table in info]
+    for d in domains:
+        d.connect(bases, offsets)
