@@ -67,6 +67,16 @@ WORKLOADS = {
     # configs[3] at its named size on one GPU (Cell = 28 B, n_max 12.5 M)
     "branching_10M": dict(model="branching", n=10_000_000, n_max=10_000_000,
                           d=0.75, dt=0.2, params={}, typed=True),
+    # configs[3] for real: branching cell + division + one protrusion per cell
+    # rewired every step (Grid::build + curand) pulling through link_forces
+    "branching_growth_1M": dict(model="branching_growth", n=1_000_000,
+                                n_max=2_097_152, d=0.75, dt=0.2,
+                                params={"mes_rate": 0.006, "epi_rate": 0.006,
+                                        "seed": 4}, typed=True),
+    "branching_growth_10M": dict(model="branching_growth", n=10_000_000,
+                                 n_max=12_582_912, d=0.75, dt=0.2,
+                                 params={"mes_rate": 0.006, "epi_rate": 0.006,
+                                         "seed": 4}, typed=True),
     "growth_100k": dict(model="growth", n=100_000, n_max=262_144, d=0.75,
                         dt=0.2, params={"prolif_rate": 0.006, "mean_dist": 0.75,
                                         "seed": 2}, typed=True),
@@ -186,7 +196,8 @@ class ClockSampler:
 # include their MUFU expansions). The growth functor bends only epithelium-
 # epithelium pairs, a thin shell of the tissue.
 FUNCTOR_LANE_INSTR = {"relu_grid": 12, "spring_grid": 8, "protrusions": 12,
-                      "growth": 20, "epithelium": 250, "branching": 270}
+                      "growth": 20, "epithelium": 250, "branching": 270,
+                      "branching_growth": 270}
 
 
 def pair_statistics(X, cube_size=1.0, sample=200_000):
@@ -262,9 +273,11 @@ def pin_to_gpu_cpus(local_rank):
 
 def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
                    cells_total=None, e2e=True):
-    """One tissue over `world` GPUs: slabs, halo exchange, global drift. The
-    process group (NCCL) must be up when world > 1. Returns the bench record on
-    rank 0 (None elsewhere)."""
+    """One tissue over `world` GPUs: bricks (slabs for 2, 2x2x1 for 4, 2x2x2 for
+    8), halo exchange, migration and drift sum by the library's own kernels over
+    peer memory (include/b200/domain.cuh); torch.distributed only carries the
+    CUDA IPC handles at set-up. The process group must be up when world > 1.
+    Returns the bench record on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
     from yalla_b200 import dd
@@ -276,61 +289,61 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
 
     d, dt = spec["d"], spec["dt"]
     n_target = cells_total or spec["cells_per_gpu"] * world
-    radius = (n_target * d ** 3 / np.sqrt(2.0) * 3.0 / (4.0 * np.pi)) ** (1.0 / 3.0)
+    density = np.sqrt(2.0) / d ** 3  # FCC with nearest-neighbour distance d
+    radius = (n_target / density * 3.0 / (4.0 * np.pi)) ** (1.0 / 3.0)
     gs = int(np.ceil(2 * (radius + d))) + 4
     gs += gs % 2
-    bounds = [-np.inf] + dd.ball_slab_cuts(radius, world) + [np.inf]
-    mine = dd.lattice_ball_slab(radius, d, bounds[rank], bounds[rank + 1],
-                                np.random.default_rng(1000 + rank))
-    face_cells = int(1.5 * np.pi * radius ** 2 * np.sqrt(2) / d ** 3)
-    n_max = int(len(mine) * 1.05) + 2 * face_cells + 1024
+    bricks = dd.brick_grid_for(world)
+    cuts = dd.ball_brick_cuts(radius, bricks)
+    # a face is at most the ball's cross-section divided among the bricks that
+    # tile it; its halo strip is 1.5 cubes thick
+    across = sorted(bricks)
+    face_cells = int(np.pi * radius ** 2 / (across[0] * across[1]) * 1.5 * density)
+    n_faces = sum(1 for b in bricks if b > 1) * (2 if max(bricks) > 2 else 1)
+    n_max = int(n_target / world * 1.08) + n_faces * int(face_cells * 1.2) + 4096
     lib = yb.product()
-    domain = dd.SlabDomain(lib, spec["model"], n_max, gs, 1.0, bounds[rank],
-                           bounds[rank + 1], "cuda",
-                           halo_capacity=face_cells * 13 // 10 + 4096)
-    domain.set_cells(mine)
+    domain = dd.BrickDomain(lib, spec["model"], n_max, gs, 1.0, bricks, cuts, rank,
+                            world, face_capacity=int(face_cells * 1.3) + 4096)
+    domain.connect_over_ipc()
+    n_seeded = domain.seed_lattice_ball(radius, d, seed=20261017)
+    assert n_seeded <= n_max, (n_seeded, n_max)
     sampler = ClockSampler(local_rank, 0.05)
-    for _ in range(warmup):
-        domain.step(dt)
+    domain.step(dt, warmup)
 
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     start.record()
-    for _ in range(steps):
-        domain.step(dt)
+    domain.step(dt, steps)
     stop.record()
     barrier()
     clocks = sampler.stop()
     ms = start.elapsed_time(stop)
-    n_mine = domain.n_owned
+    n_mine, with_ghosts, problems = domain.counts()
 
     # end to end: host buffers in and out every step
     e2e_seconds, e2e_steps, n_out = 0.0, 0, 0
     if e2e:
-        host_X = torch.from_numpy(mine).pin_memory()
+        host_X = domain.owned_state()[0].cpu().pin_memory()
         e2e_steps = max(2, steps // 4)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             domain.set_cells(host_X)
             domain.step(dt)
-            X_out, _ = domain.owned_state()
-            host_out = X_out.cpu()
+            host_out = domain.owned_state()[0].cpu()
         barrier()
         e2e_seconds = time.perf_counter() - t0
         n_out = len(host_out)
 
     # the dominant kernel, timed alone
     domain.sim.profile_sweeps(True)
-    for _ in range(3):
-        domain.step(dt)
+    domain.step(dt, 3)
     sweep_ms, sweep_launches = domain.sim.read_sweep_profile()
     domain.sim.profile_sweeps(False)
-    owned, with_ghosts, problems = domain.counts()
 
     stats = torch.tensor([ms, e2e_seconds, float(n_mine), float(n_out),
-                          float(with_ghosts - owned)],
+                          float(with_ghosts - n_mine), float(problems)],
                          dtype=torch.float64, device="cuda")
     if world > 1:
         worst = stats.clone()
@@ -338,7 +351,8 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         ms, e2e_seconds = float(worst[0]), float(worst[1])
     cells_total = int(stats[2])
-    ghosts_total = int(stats[4])
+    ghosts_total, problems = int(stats[4]), int(stats[5])
+    barrier()
     domain.close()
     if rank != 0:
         return None
@@ -348,6 +362,7 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
     avg_ms = sweep_ms / max(sweep_launches, 1)
     achieved = with_ghosts * (2 * 12 + 12) / (avg_ms * 1e-3) / 1e9
     value = cells_total * steps / (ms * 1e-3)
+    record = 4 * (yb.MODEL_LANES[spec["model"]] + 3)
     line = {
         "metric": "Heun-step cell-updates/s (Grid_solver)", "value": value,
         "unit": "cell-updates/s", "n_gpus": world, "steps": steps,
@@ -357,22 +372,25 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
         "config": {"workload": workload, "model": spec["model"],
                    "cells_total": cells_total,
                    "cells_per_gpu": cells_total // world, "grid_size": gs,
-                   "dt": dt, "parallelism": f"z-slabs x{world}, halo exchange "
-                   "+ migration over NCCL send/recv, drift all-reduce",
-                   "tissue": "jittered FCC ball, shuffled order, seeded",
+                   "dt": dt, "parallelism": "bricks %dx%dx%d, halo exchange + "
+                   "migration + drift sum by kernels over peer memory (NVLink "
+                   "P2P), no NCCL in a step" % bricks,
+                   "tissue": "jittered FCC ball, seeded on the device",
                    "l2": "working set (>1 GB per rank) exceeds the 126 MB L2"},
         "clocks": clocks,
         "ghost_cells": ghosts_total,
+        # two halo rounds per step: every ghost record crosses NVLink twice
+        "nvlink_bytes_per_step": 2 * ghosts_total * record,
         "roofline": {"bound": "hbm", "kernel": "sweep_cubes",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None,
                      "avg_launch_ms": avg_ms,
                      "share_of_step": 2 * avg_ms / (ms / steps),
                      "note": "rank 0; instruction-issue bound, see DESIGN.md"},
-        # per step: 3 pack rounds (flags, 2-3 scans, pack, [compact]), 3
-        # unpacks (+ commit), 2 x (bin, scan, place, reorder, sweep), 2 x
-        # (set_drift, update) on every rank
-        "gpu_launches": 35 * steps * world,
+        # per step and rank: 3 x (dd_select, dd_wait), 2 x dd_append_ghosts,
+        # 2 x (bin, scan, place, settle, sweep, dd_allreduce_drift, update),
+        # dd_merge, commit
+        "gpu_launches": 24 * steps * world,
         "problems": problems,
     }
     if e2e:
@@ -672,7 +690,7 @@ def main():
         if rank == 0:
             decomposed = {key: record[key] for key in (
                 "value", "unit", "n_gpus", "steps", "ms_per_step", "ghost_cells",
-                "problems", "config")}
+                "nvlink_bytes_per_step", "problems", "config")}
             decomposed["sweep_ms_per_launch"] = record["roofline"]["avg_launch_ms"]
         if world == 1 and os.environ.get("YALLA_BENCH_STRONG", "1") != "0":
             whole = run_decomposed(3, 3, dd_spec, "sphere_dd", 0, local_rank, 1,
@@ -690,7 +708,8 @@ def main():
     # minus bin_cells (fused into the predictor), corrector_step; models with a
     # counter reset add zero_cells per stage, the growth model snapshot_count
     # and proliferate
-    launches_per_step = 11 + {"growth": 4, "branching": 2}.get(spec["model"], 0)
+    launches_per_step = 11 + {"growth": 4, "branching": 2,
+                              "branching_growth": 18}.get(spec["model"], 0)
     line = {
         "metric": "Heun-step cell-updates/s (Grid_solver)",
         "value": value, "unit": "cell-updates/s", "n_gpus": world,

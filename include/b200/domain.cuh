@@ -345,7 +345,10 @@ __global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
         read_record(in.buffer[p] + SLAB_HEADER + size_t(r - s_start[p]) * W, P, v,
             n + r);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d_n = n + total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *d_n = n + total;
+        ctl->n_ghosts = total;
+    }
 }
 
 // Migration, step 2: owned cells := stayers, then the arrivals peer by peer.

@@ -54,6 +54,16 @@ inline int sm_count()
 }
 
 
+// Make sure a kernel's code is resident (CUDA loads modules lazily, on the first
+// launch, which can wait for the device to drain).
+template<typename Kernel>
+inline void load_kernel(Kernel kernel)
+{
+    cudaFuncAttributes attributes;
+    YB_CUDA(cudaFuncGetAttributes(&attributes, kernel));
+}
+
+
 // ---- device-resident control block ---------------------------------------
 // One per solver/grid; lives in device memory so that a captured CUDA graph
 // can be replayed without the host knowing n, the scan epoch, or the drift.
@@ -65,7 +75,7 @@ struct Step_ctl {
     int out_of_grid;      // cells whose cube id had to be clamped (diagnostic)
     int n_snapshot;       // n used by the step in flight (diagnostic)
     int list_overflow;    // a neighbour list of the split sweep was too short
-    int pad1;
+    int n_ghosts;         // ghosts appended by the last halo round (diagnostic)
     float drift[2][4];    // per Heun stage: mean (or fixed-point) dX.xyz
     // Domain decomposition (b200/slab.cuh): cells with an id >= n_owned are
     // ghosts -- neighbours only; in force while external_drift is set.
@@ -514,12 +524,14 @@ __global__ void __launch_bounds__(256) fill_cube_ranges(
     }
 }
 
-__global__ void __launch_bounds__(256) publish_grid(const int n,
+__global__ void __launch_bounds__(256) publish_grid(
+    const int* __restrict__ d_n, int n_max,
     const int* __restrict__ key, const int* __restrict__ offset,
     const int* __restrict__ slot_id, int* __restrict__ d_cube_id,
     int* __restrict__ d_point_id, int* __restrict__ d_cube_start,
     int* __restrict__ d_cube_end)
 {
+    const int n = live_cells(d_n, n_max);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n;
          k += gridDim.x * blockDim.x) {
         const int id = __ldg(slot_id + k);

@@ -587,6 +587,14 @@ __global__ void __launch_bounds__(
 // kernel, which is always launched behind it and returns at once otherwise.
 constexpr int LIST_MAX = 64;
 
+// Walk the cells of a chunk by descending list length, so that the lanes of a
+// warp get lists of about equal length. Measured (profiles/r02_sweep_tuning.md):
+// no gain -- the sweep waits on the functor's memory chain, not on idle lanes,
+// and the permuted cell order costs locality -- so it is off.
+#ifndef YB_INTERACT_BALANCE
+#define YB_INTERACT_BALANCE 0
+#endif
+
 struct List_config {  // list_cubes: the float3 budget of the fused sweep
     static constexpr int stage_cap = 1024;
     static constexpr int list_cap = 24;
@@ -614,9 +622,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
     __shared__ int s_row_lo[SWEEP_ROWS];
     __shared__ int s_row_v[SWEEP_ROWS + 1];
     __shared__ __align__(8) uint64_t s_bar;
+#if YB_INTERACT_BALANCE
     // balancing of interact_lists: cells per list length, per warp
     __shared__ unsigned char s_hist[SWEEP_THREADS / 32][LIST_MAX + 1];
     __shared__ unsigned char s_longer[LIST_MAX + 2];
+#endif
 
     const int t = threadIdx.x;
     const int n = live_cells(d_n, n_max);
@@ -643,8 +653,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
             s_row_lo[t] = lo;
             s_row_v[t + 1] = hi > lo ? hi - lo : 0;
         }
+#if YB_INTERACT_BALANCE
         for (int q = t; q < (SWEEP_THREADS / 32) * (LIST_MAX + 1); q += SWEEP_THREADS)
             (&s_hist[0][0])[q] = 0;
+#endif
         float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
         int my_cube = 0;
         if (live) {
@@ -754,6 +766,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
         if (live) nb_count[k] = n_listed;
         if (n_listed > LIST_MAX) ctl->list_overflow = 1;
 
+#if YB_INTERACT_BALANCE
         // Which cell of the chunk thread q of interact_lists takes: the cells
         // in order of DESCENDING list length (ties: ascending slot), so that
         // the lanes of a warp walk lists of about the same length -- a warp
@@ -784,15 +797,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
         for (int w = 0; w < warp_id; w++) position += s_hist[w][key];
         if (first_slot + position < nb_stride)
             nb_order[first_slot + position] = static_cast<unsigned char>(t);
+#endif
         __syncthreads();  // the next chunk reuses every shared array
     }
 }
 
 #ifndef YB_INTERACT_CTAS
 #define YB_INTERACT_CTAS 6
-#endif
-#ifndef YB_INTERACT_BALANCE  // walk the cells of a chunk by descending list length
-#define YB_INTERACT_BALANCE 1
 #endif
 #ifndef YB_INTERACT_PREFETCH  // gather partner e + 1 while pair e is evaluated
 #define YB_INTERACT_PREFETCH 1

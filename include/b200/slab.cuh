@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(256) slab_append_ghosts(Step_ctl* ctl,
                      : recv_hi + SLAB_HEADER + size_t(r - n_lo) * W;
         read_record(record, P, v, n + r);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d_n = n + n_lo + n_hi;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *d_n = n + n_lo + n_hi;
+        ctl->n_ghosts = n_lo + n_hi;
+    }
 }
 
 // Migration, step 2: owned cells := stayers, arrivals from below, from above.

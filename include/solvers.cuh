@@ -488,16 +488,19 @@ public:
                 d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
         YB_CUDA(cudaGetLastError());
     }
-    // Blocking: owned cells, owned + ghost cells, and the number of problems seen
+    // Blocking: owned cells, owned + ghost cells of the last halo round, and the
+    // number of problems seen
     // (cells outside the grid; exchange-buffer overflows count 2^20 each).
     void slab_counts(int* n_owned, int* n_total, int* problems)
     {
         yb::Step_ctl snapshot;
         YB_CUDA(cudaMemcpyAsync(&snapshot, d_ctl, sizeof(snapshot),
             cudaMemcpyDeviceToHost, stream));
-        const int total = get_d_n();
+        get_d_n();  // waits for the stream
         if (n_owned) *n_owned = snapshot.n_owned;
-        if (n_total) *n_total = total;
+        // ghosts only live from a halo round to the end of its stage: report
+        // how many the last round brought
+        if (n_total) *n_total = snapshot.n_owned + snapshot.n_ghosts;
         if (problems) *problems = snapshot.out_of_grid;
     }
 
@@ -524,6 +527,23 @@ public:
     void dom_step(float dt)
     {
         assert(dom.active && dom.connected());
+        // With lazy module loading the first launch of a kernel may wait for the
+        // device to drain -- while a dd_wait on it spins for a neighbour whose
+        // kernels this very thread has yet to enqueue (bricks sharing a process)
+        // or merely late (one process per GPU). Load everything up front.
+        static const bool loaded = [] {
+            yb::load_kernel(yb::dd_select<Pt>);
+            yb::load_kernel(yb::dd_wait);
+            yb::load_kernel(yb::dd_append_ghosts<Pt>);
+            yb::load_kernel(yb::dd_merge<Pt>);
+            yb::load_kernel(yb::dd_allreduce_drift);
+            yb::load_kernel(yb::slab_commit_count);
+            yb::load_kernel(yb::predictor_step<Pt, false>);
+            yb::load_kernel(yb::corrector_step<Pt>);
+            Computer<Pt>::template load_kernels<pw_int, pw_friction, false>();
+            return true;
+        }();
+        (void)loaded;
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         for (int stage = 0; stage < 2; stage++) {
             Pt* X_stage = stage == 0 ? d_X : d_X1;
@@ -871,6 +891,11 @@ protected:
 
     const float4* dd_cube_order() const { return nullptr; }
 
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    static void load_kernels()
+    {}
+
     // nothing to prepare ahead of the generic forces
     void index_ahead(
         cudaStream_t, const int*, const Pt*, const float3*, yb::Step_ctl*)
@@ -1045,24 +1070,31 @@ public:
         const int n, const Pt* __restrict__ d_X, const float cube_size = 1)
     {
         assert(n <= n_max);
+        YB_CUDA(cudaMemcpyAsync(
+            d_n_scratch, &n, sizeof(int), cudaMemcpyHostToDevice, stream));
+        build_live(d_n_scratch, d_X, cube_size);
+    }
+    // Extension: the same with the number of points read from device memory
+    // (e.g. Solution::d_n) -- no host round trip, capturable into a CUDA graph.
+    template<typename Pt>
+    void build_live(const int* d_n_points, const Pt* __restrict__ d_X,
+        const float cube_size = 1)
+    {
         const cudaStream_t s = stream;
         const int sms = yb::sm_count();
-        YB_CUDA(cudaMemcpyAsync(
-            d_n_scratch, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+        const int blocks = yb::stride_grid(n_max, 256, sms);
         yb::fill_cube_ranges<<<yb::stride_grid(n_cubes, 256, sms), 256, 0, s>>>(
             n_cubes, d_cube_start, d_cube_end);
-        if (n > 0) {
-            const int blocks = yb::stride_grid(n, 256, sms);
-            yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n_scratch, n_max, d_X,
-                cube_size, yb::Grid_box::cubic(grid_size), sort.key,
-                sort.arrival, sort.count, d_ctl);
-            yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
-                sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
-            yb::place_ids<<<blocks, 256, 0, s>>>(d_n_scratch, n_max, sort.key,
-                sort.arrival, sort.offset, sort.slot_id);
-            yb::publish_grid<<<blocks, 256, 0, s>>>(n, sort.key, sort.offset,
-                sort.slot_id, d_cube_id, d_point_id, d_cube_start, d_cube_end);
-        }
+        yb::bin_cells<Pt><<<blocks, 256, 0, s>>>(d_n_points, n_max, d_X,
+            cube_size, yb::Grid_box::cubic(grid_size), sort.key, sort.arrival,
+            sort.count, d_ctl);
+        yb::scan_bins<<<sort.n_tiles, yb::SCAN_THREADS, 0, s>>>(
+            sort.count, sort.offset, sort.n_tiles, sort.status, d_ctl);
+        yb::place_ids<<<blocks, 256, 0, s>>>(d_n_points, n_max, sort.key,
+            sort.arrival, sort.offset, sort.slot_id);
+        yb::publish_grid<<<blocks, 256, 0, s>>>(d_n_points, n_max, sort.key,
+            sort.offset, sort.slot_id, d_cube_id, d_point_id, d_cube_start,
+            d_cube_end);
         YB_CUDA(cudaGetLastError());
     }
     template<typename Pt, template<typename> class Solver>
@@ -1199,6 +1231,21 @@ protected:
             return resident < 1 ? 1 : resident;
         }();
         return ctas_per_sm;
+    }
+
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    static void load_kernels()
+    {
+        yb::load_kernel(yb::bin_cells<Pt>);
+        yb::load_kernel(yb::scan_bins);
+        yb::load_kernel(yb::place_ids);
+        yb::load_kernel(yb::reorder_cells<Pt>);
+        yb::load_kernel(yb::place_cells<Pt>);
+        yb::load_kernel(yb::settle_cells<Pt>);
+        yb::load_kernel(yb::list_cubes);
+        yb::load_kernel(yb::interact_lists<Pt, pw_int, pw_friction, SEEDED>);
+        yb::load_kernel(yb::sweep_cubes<Pt, pw_int, pw_friction, SEEDED>);
     }
 
     // Points with extra lanes run the sweep as two kernels (b200/pair_sweep.cuh,

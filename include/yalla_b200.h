@@ -66,6 +66,13 @@ const char* yb_last_error(void);
  *                                     link_forces as generic force, relu_force
  *  "branching"    Cell (7)    Grid    examples/branching.cu:57-110
  *                                     epi_turing_mes_noturing + counters
+ *  "branching_growth" Cell (7) Grid   the same cell with division
+ *                                     (branching.cu:113-138) and one protrusion
+ *                                     per cell rewired every step
+ *                                     (intercalation_w_gradient.cu:119-173,
+ *                                     Grid::build + curand) pulling through
+ *                                     link_forces: BASELINE.json configs[3].
+ *                                     GPU libraries only (needs curand).
  *
  * grid_size / cube_size are the Grid_solver constructor arguments
  * (solvers.cuh:469) and are ignored by Tile models. */
@@ -106,8 +113,11 @@ int yb_sim_get_ints(yb_sim* sim, const char* name, int* h_values, int capacity);
 int yb_sim_seed_sphere(yb_sim* sim, int n, float dist_to_nb,
     unsigned long long seed, int relax_steps);
 
-/* Links of models that have them: pairs (a, b) as 2 * n_links ints. */
+/* Links of models that have them: pairs (a, b) as 2 * n_links ints. get_links
+ * waits for the model's stream and copies the current links back
+ * (Links::copy_to_host). */
 int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links);
+int yb_sim_get_links(yb_sim* sim, int* h_links, int capacity, int* n_out);
 
 /* Enqueue n_steps model steps of size dt. Does not wait for them. */
 int yb_sim_step(yb_sim* sim, float dt, int n_steps);

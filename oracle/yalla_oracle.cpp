@@ -1040,6 +1040,10 @@ int yb_sim_step_host_async(
 {
     return fail(YB_ENOSYS, "asynchronous steps need the product library");
 }
+int yb_sim_get_links(yb_sim*, int*, int, int*)
+{
+    return fail(YB_ENOSYS, "reading links back: GPU libraries only");
+}
 int yb_dom_begin(yb_sim*, int, int, const float*, const float*, float,
     const int*, const int*, const int*, const int*)
 {

@@ -63,6 +63,10 @@ def test_product_package_does_not_touch_the_oracle():
 
 def test_model_table_matches_oracle(oracle):
     for model, lanes in yb.MODEL_LANES.items():
+        if model in yb.GPU_ONLY_MODELS:
+            with pytest.raises(yb.YallaError, match="unknown model"):
+                oracle.sim(model, 8)
+            continue
         with oracle.sim(model, 8) as sim:
             assert sim.lanes == lanes
             assert sim.n_max == 8

@@ -1,0 +1,93 @@
+"""BASELINE.json configs[3] on the GPU: the branching cell with division and one
+protrusion per cell rewired every step ("branching_growth": examples/branching.cu
++ examples/intercalation_w_gradient.cu:119-173), product vs the reference build.
+
+Link topology is integer work: with the same curand seeds the first rewiring
+must produce the very same links in both builds. With division on, later steps
+are compared on ensemble statistics from equal seeds (north_star).
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_states_close
+from yalla_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def tissue(n, seed):
+    rng = np.random.default_rng(seed)
+    X = np.zeros((n, 7), dtype=np.float32)
+    X[:, :5] = workloads.polarized_ball(n, 0.75, rng, lattice=True, noise=0.0)
+    X[:, 5:] = rng.random((n, 2)).astype(np.float32) * 0.2
+    types = workloads.shell_types(X)
+    X[types == 0, 3:5] = 0
+    return X, types
+
+
+def run(lib, X, types, n_max, gs, steps, dt, seed, mes_rate, epi_rate):
+    with lib.sim("branching_growth", n_max, gs, 1.0) as sim:
+        sim.set_param("seed", seed)
+        sim.set_param("mes_rate", mes_rate)
+        sim.set_param("epi_rate", epi_rate)
+        sim.set_ints("type", types)
+        sim.set_state(X)
+        series = []
+        for _ in range(steps):
+            sim.step(dt, 1)
+            series.append(sim.n())
+        return {"X": sim.get_state(), "links": sim.get_links(),
+                "mes_nbs": sim.get_ints("mes_nbs"), "n": series}
+
+
+def test_first_rewiring_is_bit_exact_vs_reference(product, reference):
+    n = 40_000
+    X, types = tissue(n, 51)
+    gs = workloads.grid_size_for(n, 0.75)
+    out = [run(lib, X, types, n, gs, 1, 0.1, 9, 0.0, 0.0)
+           for lib in (product, reference)]
+    assert len(out[0]["links"]) == n
+    live = out[1]["links"][:, 0] != out[1]["links"][:, 1]
+    assert live.sum() > 0.2 * (types == 0).sum()   # mesenchyme grew protrusions
+    assert np.array_equal(out[0]["links"], out[1]["links"])
+    assert np.array_equal(out[0]["mes_nbs"], out[1]["mes_nbs"])
+    assert_states_close(out[0]["X"][:, :3], out[1]["X"][:, :3], 1, "positions")
+
+
+def test_no_division_run_matches_reference(product, reference):
+    # rewiring draws from curand but the draws are per link and the grid is
+    # bit-exact, so without division both builds see the same random choices
+    n, steps = 40_000, 5
+    X, types = tissue(n, 52)
+    gs = workloads.grid_size_for(n, 0.75)
+    out = [run(lib, X, types, n, gs, steps, 0.1, 3, 0.0, 0.0)
+           for lib in (product, reference)]
+    same = np.all(out[0]["links"] == out[1]["links"], axis=1).mean()
+    assert same > 0.999   # a rewiring test within an ulp of its threshold may flip
+    assert_states_close(out[0]["X"][:, :3], out[1]["X"][:, :3], steps, "positions",
+                        4.0)
+
+
+def test_ensemble_statistics_match_reference(product, reference):
+    n0, n_max, steps = 20_000, 40_000, 20
+    X, types = tissue(n0, 53)
+    gs = workloads.grid_size_for(n0, 0.75, growth=2.0)
+    stats = {}
+    for name, lib in (("product", product), ("reference", reference)):
+        counts, gyration, linked = [], [], []
+        for seed in range(6):
+            out = run(lib, X, types, n_max, gs, steps, 0.1, seed, 0.01, 0.01)
+            state = out["X"].astype(np.float64)
+            assert np.all(np.isfinite(state))
+            counts.append(out["n"][-1])
+            centred = state[:, :3] - state[:, :3].mean(axis=0)
+            gyration.append(np.sqrt((centred ** 2).sum(axis=1).mean()))
+            links = out["links"]
+            linked.append(np.mean(links[:, 0] != links[:, 1]))
+        stats[name] = (np.array(counts, dtype=np.float64), np.array(gyration),
+                       np.array(linked))
+    (n_a, rg_a, l_a), (n_b, rg_b, l_b) = stats["product"], stats["reference"]
+    assert np.all(n_a > n0)
+    assert abs(n_a.mean() - n_b.mean()) < 0.01 * n_b.mean()
+    assert abs(rg_a.mean() - rg_b.mean()) < 0.005 * rg_b.mean()
+    assert abs(l_a.mean() - l_b.mean()) < 0.02

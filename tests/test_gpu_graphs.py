@@ -56,6 +56,14 @@ with lib.sim("branching", 30000, gs, 1.0) as sim:
     sim.step(0.1, 5)
     out["branching"] = sim.get_state()
     out["branching_epi"] = sim.get_ints("epi_nbs")
+with lib.sim("branching_growth", 60000, gs, 1.0) as sim:
+    sim.set_param("mes_rate", 0.0)
+    sim.set_param("epi_rate", 0.0)
+    sim.set_ints("type", types)
+    sim.set_state(X7)
+    sim.step(0.1, 5)
+    out["config3"] = sim.get_state()
+    out["config3_links"] = sim.get_links()
 Xp = workloads.lattice_ball(20000, 0.8, np.random.default_rng(5))
 links = workloads.random_links(Xp, 30000, 2.0, np.random.default_rng(6))
 with lib.sim("protrusions", 20000, 40, 1.0) as sim:

@@ -60,6 +60,8 @@ SIGNATURES = {
                                           ctypes.c_int]),
     "yb_sim_set_links": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_int]),
+    "yb_sim_get_links": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, _c_int_p]),
     "yb_sim_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
                                    ctypes.c_int]),
     "yb_sim_step_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float,
@@ -140,8 +142,10 @@ SIGNATURES = {
 MODEL_LANES = {
     "springs": 3, "spring_tile": 3, "spring_grid": 3, "relu_tile": 3,
     "relu_grid": 3, "protrusions": 3, "epithelium": 5, "growth": 5,
-    "branching": 7,
+    "branching": 7, "branching_growth": 7,
 }
+# models that draw from curand: no CPU oracle
+GPU_ONLY_MODELS = {"branching_growth"}
 
 
 class YallaError(RuntimeError):
@@ -314,6 +318,14 @@ class Sim:
         links = _i32(links).reshape(-1, 2)
         self.lib.check(self.lib.cdll.yb_sim_set_links(
             self.handle, links.ctypes.data, len(links)), "set_links")
+
+    def get_links(self, capacity=None):
+        capacity = capacity or 4 * self.n_max
+        out = np.zeros((capacity, 2), dtype=np.int32)
+        n = ctypes.c_int()
+        self.lib.check(self.lib.cdll.yb_sim_get_links(
+            self.handle, out.ctypes.data, capacity, ctypes.byref(n)), "get_links")
+        return out[:n.value].copy()
 
     def step(self, dt, n_steps=1):
         self.lib.check(self.lib.cdll.yb_sim_step(self.handle, dt, n_steps),

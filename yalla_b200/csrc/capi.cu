@@ -66,6 +66,10 @@ struct yb_sim {
     {
         return fail(YB_EINVAL, "model has no links");
     }
+    virtual int get_links(int* h_links, int capacity, int* n_out)
+    {
+        return fail(YB_EINVAL, "model has no links");
+    }
     // One model step (asynchronous).
     virtual int step(float dt) = 0;
     // Host buffers in, n_steps steps, host buffers out; waits.
@@ -306,7 +310,11 @@ struct Sim_base : yb_sim {
         cudaStreamDestroy(pipe.down);
         pipe.up = pipe.down = nullptr;
     }
-    ~Sim_base() override { close_pipeline(); }
+    ~Sim_base() override
+    {
+        close_recording();
+        close_pipeline();
+    }
 
     // Enqueue upload, steps and the download of `out_cells` cells plus the
     // count (into pinned *h_n_out); yb_sim_host_drain waits for all of it.
@@ -388,6 +396,57 @@ struct Sim_base : yb_sim {
     {
         cells.read_sweep_profile(total_ms, launches);
         return YB_OK;
+    }
+
+    // ---- a whole model iteration as one CUDA graph ---------------------------
+    // Models whose iteration is more than take_step (division, rewiring of
+    // links, ...) record it once per dt on a side stream -- the solver issues
+    // its stages into the recording (capturable generic forces) -- and replay
+    // it with one graph launch. The first iteration runs directly, so that
+    // kernel attributes and scratch are set up outside any recording.
+    virtual void enqueue_iteration(float dt) {}
+    cudaGraphExec_t iteration = nullptr;
+    float iteration_dt = 0.f;
+    bool warmed_up = false;
+    cudaStream_t recording_stream = nullptr;
+
+    void drop_iteration()
+    {
+        if (iteration == nullptr) return;
+        cudaStreamSynchronize(model_stream());
+        cudaGraphExecDestroy(iteration);
+        iteration = nullptr;
+    }
+    void close_recording()
+    {
+        drop_iteration();
+        if (recording_stream) cudaStreamDestroy(recording_stream);
+        recording_stream = nullptr;
+    }
+    int replay_iteration(float dt)
+    {
+        if (!yb::graphs_enabled() || profiling_sweeps || !warmed_up) {
+            warmed_up = true;
+            enqueue_iteration(dt);
+            return 0;
+        }
+        if (iteration == nullptr || iteration_dt != dt) {
+            drop_iteration();
+            if (recording_stream == nullptr)
+                cudaStreamCreateWithFlags(&recording_stream, cudaStreamNonBlocking);
+            const cudaStream_t users = cells.stream;
+            cudaGraph_t graph;
+            cudaStreamBeginCapture(recording_stream, cudaStreamCaptureModeRelaxed);
+            cells.stream = recording_stream;
+            enqueue_iteration(dt);
+            cells.stream = users;
+            cudaStreamEndCapture(recording_stream, &graph);
+            cudaGraphInstantiate(&iteration, graph, 0);
+            cudaGraphDestroy(graph);
+            iteration_dt = dt;
+        }
+        cudaGraphLaunch(iteration, model_stream());
+        return 0;
     }
 
     // ---- domain decomposition (device pointers) ---------------------------
@@ -704,6 +763,15 @@ struct Protrusion_sim : Sim_base<float3, Grid_solver> {
         links.copy_to_device();
         return check_cuda("set_links");
     }
+    int get_links(int* h_links, int capacity, int* n_out) override
+    {
+        cudaStreamSynchronize(model_stream());
+        links.copy_to_host();
+        if (*links.h_n > capacity) return fail(YB_EINVAL, "capacity < n_links");
+        memcpy(h_links, links.h_link, sizeof(Link) * size_t(*links.h_n));
+        if (n_out) *n_out = *links.h_n;
+        return check_cuda("get_links");
+    }
     int step(float dt) override
     {
         auto pull = [this](const int n, const float3* __restrict__ d_X,
@@ -868,10 +936,6 @@ struct Growth_sim : Typed_sim<Po_cell> {
     }
     ~Growth_sim() override
     {
-#ifdef YALLA_B200
-        drop_iteration();
-        if (recording_stream) cudaStreamDestroy(recording_stream);
-#endif
         cudaFree(d_n_at_launch);
         cudaFree(d_state);
     }
@@ -901,6 +965,9 @@ struct Growth_sim : Typed_sim<Po_cell> {
     }
     // What examples/passive_growth.cu does per iteration on the device.
     void enqueue_iteration(float dt)
+#ifdef YALLA_B200
+        override
+#endif
     {
         const int n_max = cells.n_max;
         auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
@@ -940,53 +1007,15 @@ struct Growth_sim : Typed_sim<Po_cell> {
             return 0;
         }
         // The whole iteration -- both Heun stages with the counter resets as
-        // (capturable) generic force, then the division kernels -- is recorded
-        // once per (dt, parameters) on a side stream, with the solver issuing
-        // its stages into the recording, and replayed with one graph launch.
-        // reset_counters is handed n_max there: clearing the counters of dead
-        // slots as well is harmless. The first iteration runs directly (kernel
-        // attributes are set up outside any recording).
-        if (yb::graphs_enabled() && !profiling_sweeps && warmed_up) {
-            if (iteration == nullptr || iteration_dt != dt) record_iteration(dt);
-            cudaGraphLaunch(iteration, model_stream());
-            return 0;
-        }
-        warmed_up = true;
-#endif
+        // (capturable) generic force, then the division kernels -- replays
+        // from one graph. reset_counters is handed n_max there: clearing the
+        // counters of dead slots as well is harmless.
+        return replay_iteration(dt);
+#else
         enqueue_iteration(dt);
         return 0;
-    }
-
-#ifdef YALLA_B200
-    cudaGraphExec_t iteration = nullptr;
-    float iteration_dt = 0.f;
-    bool warmed_up = false;
-    cudaStream_t recording_stream = nullptr;
-
-    void drop_iteration()
-    {
-        if (iteration == nullptr) return;
-        cudaStreamSynchronize(model_stream());
-        cudaGraphExecDestroy(iteration);
-        iteration = nullptr;
-    }
-    void record_iteration(float dt)
-    {
-        drop_iteration();
-        if (recording_stream == nullptr)
-            cudaStreamCreateWithFlags(&recording_stream, cudaStreamNonBlocking);
-        const cudaStream_t users = cells.stream;
-        cudaGraph_t graph;
-        cudaStreamBeginCapture(recording_stream, cudaStreamCaptureModeRelaxed);
-        cells.stream = recording_stream;
-        enqueue_iteration(dt);
-        cells.stream = users;
-        cudaStreamEndCapture(recording_stream, &graph);
-        cudaGraphInstantiate(&iteration, graph, 0);
-        cudaGraphDestroy(graph);
-        iteration_dt = dt;
-    }
 #endif
+    }
 };
 
 // ---- 7-float branching cell --------------------------------------------------------
@@ -1011,6 +1040,129 @@ struct Branching_sim : Typed_sim<models::Cell> {
                              models::Cell* d_dX) { reset_counters(n); };
         cells.take_step<models::epi_turing_mes_noturing>(dt, reset_nbs);
         return 0;
+    }
+};
+
+// ---- branching cell + division + protrusions rewired every step ----------------
+// BASELINE.json configs[3]: per iteration the neighbour grid
+// of the cells is rebuilt (Grid::build, cube size r_protrusion), one protrusion
+// per cell is rewired at random among its neighbours (update_protrusions,
+// curand), the tissue takes a Heun step with counter reset + link_forces as
+// generic force, and cells divide (proliferate_branching, curand).
+struct Branching_growth_sim : Typed_sim<models::Cell> {
+    Links protrusions;
+    Grid grid;
+    curandState* d_state = nullptr;
+    int* d_n_at_launch = nullptr;
+    float mes_rate = 0.006f, epi_rate = 0.006f, mean_dist = 0.75f;
+    int seed = 4;
+    bool seeded = false;
+
+    Branching_growth_sim(int n_max, int grid_size, float cube_size)
+        : Typed_sim<models::Cell>{n_max, grid_size, cube_size},
+          protrusions{n_max * models::prots_per_cell, 0.2f},
+          // cubes of edge r_protrusion = 2 cover the same volume with half the
+          // cubes per axis
+          grid{n_max, grid_size / 2 + 2}
+    {
+        cudaMalloc(&d_state, sizeof(curandState) * size_t(n_max));
+        cudaMalloc(&d_n_at_launch, sizeof(int));
+        protrusions.set_d_n(0);
+    }
+    ~Branching_growth_sim() override
+    {
+#ifdef YALLA_B200
+        close_recording();
+#endif
+        cudaFree(d_n_at_launch);
+        cudaFree(d_state);
+    }
+    int set_param(const std::string& name, double value) override
+    {
+#ifdef YALLA_B200
+        drop_iteration();  // parameters are baked into the recorded launches
+#endif
+        if (name == "mes_rate") {
+            mes_rate = static_cast<float>(value);
+        } else if (name == "epi_rate") {
+            epi_rate = static_cast<float>(value);
+        } else if (name == "mean_dist") {
+            mean_dist = static_cast<float>(value);
+        } else if (name == "link_strength") {
+            protrusions.strength = static_cast<float>(value);
+        } else if (name == "seed") {
+            seed = static_cast<int>(value);
+            seeded = false;
+        } else {
+            const int fixed = Base::set_fix(name, value);
+            return fixed <= 0 ? fixed : yb_sim::set_param(name, value);
+        }
+        return YB_OK;
+    }
+    int get_links(int* h_links, int capacity, int* n_out) override
+    {
+        cudaStreamSynchronize(model_stream());
+        protrusions.copy_to_host();
+        const int n = *protrusions.h_n;
+        if (n > capacity) return fail(YB_EINVAL, "capacity < n_links");
+        memcpy(h_links, protrusions.h_link, sizeof(Link) * size_t(n));
+        if (n_out) *n_out = n;
+        return check_cuda("get_links");
+    }
+
+    void enqueue_iteration(float dt)
+#ifdef YALLA_B200
+        override
+#endif
+    {
+        const int n_max = cells.n_max;
+        const cudaStream_t s = model_stream();
+        const int n_links_max = n_max * models::prots_per_cell;
+        // intercalation_w_gradient.cu:236-241, with the counts left on the device
+        models::set_link_count<<<1, 1, 0, s>>>(cells.d_n, protrusions.d_n);
+#ifdef YALLA_B200
+        grid.stream = s;
+        grid.build_live(cells.d_n, cells.d_X, models::r_protrusion);
+#else
+        grid.build(cells, models::r_protrusion);
+#endif
+        models::update_protrusions<<<(n_links_max + 32 - 1) / 32, 32, 0, s>>>(
+            cells.d_n, grid.d_grid, cells.d_X, protrusions.d_state,
+            protrusions.d_link);
+        auto intercalation = [this](const int n, const models::Cell* __restrict__ d_X,
+                                 models::Cell* d_dX) {
+            reset_counters(n);
+            link_forces(protrusions, d_X, d_dX);
+        };
+        cells.take_step<models::epi_turing_mes_noturing>(dt, intercalation);
+        if (mes_rate > 0 || epi_rate > 0) {
+            models::snapshot_count<<<1, 1, 0, s>>>(cells.d_n, d_n_at_launch);
+            models::proliferate_branching<<<(n_max + 128 - 1) / 128, 128, 0, s>>>(
+                mes_rate, epi_rate, mean_dist, n_max, d_state, cells.d_X,
+                cells.d_old_v, cells.d_n, d_n_at_launch);
+        }
+    }
+
+    int step(float dt) override
+    {
+        const int n_max = cells.n_max;
+        if (!seeded) {
+            // fixed seeds for both generators (the Links constructor seeds its
+            // states from the wall clock)
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, model_stream()>>>(
+                n_max, seed, d_state);
+            const int n_links_max = n_max * models::prots_per_cell;
+            setup_rand_states<<<(n_links_max + 128 - 1) / 128, 128, 0,
+                model_stream()>>>(n_links_max, seed + 1, protrusions.d_state);
+            seeded = true;
+        }
+        this->bind();
+#ifdef YALLA_B200
+        return replay_iteration(dt);
+#else
+        enqueue_iteration(dt);
+        return 0;
+#endif
     }
 };
 
@@ -1145,6 +1297,8 @@ int yb_sim_create(const char* model, int n_max, int grid_size, float cube_size,
         sim = new Growth_sim(n_max, grid_size, cube_size);
     else if (name == "branching")
         sim = new Branching_sim(n_max, grid_size, cube_size);
+    else if (name == "branching_growth")
+        sim = new Branching_growth_sim(n_max, grid_size, cube_size);
     else
         return fail(YB_EINVAL, "unknown model " + name);
     const int status = check_cuda("yb_sim_create");
@@ -1209,6 +1363,11 @@ int yb_sim_seed_sphere(yb_sim* sim, int n, float dist_to_nb,
 int yb_sim_set_links(yb_sim* sim, const int* h_links, int n_links)
 {
     return sim->set_links(h_links, n_links);
+}
+
+int yb_sim_get_links(yb_sim* sim, int* h_links, int capacity, int* n_out)
+{
+    return sim->get_links(h_links, capacity, n_out);
 }
 
 int yb_sim_step(yb_sim* sim, float dt, int n_steps)

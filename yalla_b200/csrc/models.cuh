@@ -249,4 +249,125 @@ __device__ Cell epi_turing_mes_noturing(Cell Xi, Cell r, float dist, int i, int 
     return dF;
 }
 
+
+
+// ---- branching + growth + protrusions (BASELINE.json configs[3]) --------------------
+// The branching cell with cell division (examples/branching.cu:113-138, without
+// the lineage bookkeeping) and one protrusion per cell that a kernel rewires
+// every step (examples/intercalation_w_gradient.cu:119-173), pulling through
+// link_forces. The morphogen v plays the part of that example's w (cells far
+// from the source align their protrusion along its gradient), u that of f.
+// Launches are sized for the capacity and read the live count on the device,
+// so that one iteration needs nothing from the host.
+const auto prots_per_cell = 1;
+const auto r_protrusion = 2.0f;
+
+__global__ void set_link_count(const int* d_n_cells, int* d_n_links)
+{
+    *d_n_links = *d_n_cells * prots_per_cell;
+}
+
+__global__ void update_protrusions(const int* d_n_cells,
+    const Grid* __restrict__ d_grid, const Cell* __restrict d_X,
+    curandState* d_state, Link* d_link)
+{
+    const int n_cells = *d_n_cells;
+    auto i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells * prots_per_cell) return;
+
+    auto j = static_cast<int>((i + 0.5) / prots_per_cell);
+    auto rand_nb_cube =
+        d_grid->d_cube_id[j] +
+        d_nhood[min(static_cast<int>(curand_uniform(&d_state[i]) * 27), 26)];
+    if (rand_nb_cube < 0 or rand_nb_cube >= d_grid->n_cubes) return;
+    auto cells_in_cube =
+        d_grid->d_cube_end[rand_nb_cube] - d_grid->d_cube_start[rand_nb_cube];
+    if (cells_in_cube < 1) return;
+
+    auto a = d_grid->d_point_id[j];
+    auto b =
+        d_grid->d_point_id[d_grid->d_cube_start[rand_nb_cube] +
+                           min(static_cast<int>(
+                                   curand_uniform(&d_state[i]) * cells_in_cube),
+                               cells_in_cube - 1)];
+    if (a == b) return;
+
+    if ((d_type[a] != mesenchyme) or (d_type[b] != mesenchyme)) return;
+
+    auto link = &d_link[a * prots_per_cell + i % prots_per_cell];
+
+    auto old_r = d_X[link->a] - d_X[link->b];
+    auto old_dist = norm3df(old_r.x, old_r.y, old_r.z);
+    auto new_r = d_X[a] - d_X[b];
+    auto new_dist = norm3df(new_r.x, new_r.y, new_r.z);
+    if (new_dist > r_protrusion) return;
+
+    auto not_initialized = link->a == link->b;
+    auto noise = curand_uniform(&d_state[i]);
+    auto superficial = d_X[a].v + d_X[b].v > 0.3f;
+    auto parallel_to_v_gradient = false;
+    auto normal_to_u_gradient = false;
+    if (superficial) {
+        normal_to_u_gradient =
+            fabs(new_r.u / new_dist) < fabs(old_r.u / old_dist) * (1.f - noise);
+    } else {
+        parallel_to_v_gradient =
+            fabs(new_r.v / new_dist) > fabs(old_r.v / old_dist) * (1.f - noise);
+    }
+
+    if (not_initialized or parallel_to_v_gradient or normal_to_u_gradient) {
+        link->a = a;
+        link->b = b;
+    }
+}
+
+// Division rule of examples/branching.cu:113-138 (mesenchyme at mes_rate, here
+// without the v threshold; epithelium at epi_rate where it has room and touches
+// mesenchyme); daughters halve u and v with their mothers.
+__global__ void proliferate_branching(float mes_rate, float epi_rate,
+    float mean_distance, int n_max, curandState* d_state, Cell* d_X,
+    float3* d_old_v, int* d_n_cells, const int* d_n_at_launch)
+{
+    const int n_cells = *d_n_at_launch;
+    auto i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;  // Dividing new cells is problematic!
+
+    auto rnd = curand_uniform(&d_state[i]);
+    switch (d_type[i]) {
+        case mesenchyme: {
+            if (rnd > mes_rate) return;
+
+            break;
+        }
+        case epithelium: {
+            if (d_epi_nbs[i] > 5) return;
+
+            if (d_mes_nbs[i] <= 0) return;
+
+            if (rnd > epi_rate) return;
+        }
+    }
+
+    auto n = atomicAdd(d_n_cells, 1);
+    if (n >= n_max) {  // full: undo instead of writing out of bounds
+        atomicSub(d_n_cells, 1);
+        return;
+    }
+    auto theta = acosf(2. * curand_uniform(&d_state[i]) - 1);
+    auto phi = curand_uniform(&d_state[i]) * 2 * M_PI;
+    d_X[n].x = d_X[i].x + mean_distance / 4 * sinf(theta) * cosf(phi);
+    d_X[n].y = d_X[i].y + mean_distance / 4 * sinf(theta) * sinf(phi);
+    d_X[n].u = d_X[i].u / 2;
+    d_X[n].z = d_X[i].z + mean_distance / 4 * cosf(theta);
+    d_X[i].u = d_X[i].u / 2;
+    d_X[n].v = d_X[i].v / 2;
+    d_X[i].v = d_X[i].v / 2;
+    d_X[n].theta = d_X[i].theta;
+    d_X[n].phi = d_X[i].phi;
+    d_type[n] = d_type[i];
+    d_mes_nbs[n] = 0;
+    d_epi_nbs[n] = 0;
+    d_old_v[n] = d_old_v[i];
+}
+
 }  // namespace models
