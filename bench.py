@@ -340,6 +340,8 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
     domain.sim.profile_sweeps(True)
     domain.step(dt, 3)
     sweep_ms, sweep_launches = domain.sim.read_sweep_profile()
+    phases = {name: value / 3 for name, value in
+              domain.sim.dom_read_profile().items()}
     domain.sim.profile_sweeps(False)
 
     stats = torch.tensor([ms, e2e_seconds, float(n_mine), float(n_out),
@@ -379,6 +381,7 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
                    "l2": "working set (>1 GB per rank) exceeds the 126 MB L2"},
         "clocks": clocks,
         "ghost_cells": ghosts_total,
+        "phase_ms_per_step_rank0": phases,
         # two halo rounds per step: every ghost record crosses NVLink twice
         "nvlink_bytes_per_step": 2 * ghosts_total * record,
         "roofline": {"bound": "hbm", "kernel": "sweep_cubes",
@@ -690,7 +693,8 @@ def main():
         if rank == 0:
             decomposed = {key: record[key] for key in (
                 "value", "unit", "n_gpus", "steps", "ms_per_step", "ghost_cells",
-                "nvlink_bytes_per_step", "problems", "config")}
+                "nvlink_bytes_per_step", "phase_ms_per_step_rank0", "problems",
+                "config")}
             decomposed["sweep_ms_per_launch"] = record["roofline"]["avg_launch_ms"]
         if world == 1 and os.environ.get("YALLA_BENCH_STRONG", "1") != "0":
             whole = run_decomposed(3, 3, dd_spec, "sphere_dd", 0, local_rank, 1,

@@ -25,18 +25,31 @@ namespace yb {
 
 constexpr int SLAB_HEADER = 4;  // floats in front of the records
 
+// Records are 8-byte aligned when they hold an even number of floats (the
+// header is 16 bytes): stored as float2s then -- exchange buffers may live in a
+// neighbour's memory, where every store is an NVLink transaction.
 template<typename Pt>
 __device__ __forceinline__ void write_record(
     float* record, const Pt* P, const float3* v, int i)
 {
     using L = Layout<Pt>;
+    constexpr int W = L::lanes + 3;
     const float* x = reinterpret_cast<const float*>(P + i);
     const float* w = reinterpret_cast<const float*>(v + i);
+    float r[W];
 #pragma unroll
-    for (int k = 0; k < L::lanes; k++) record[k] = x[k];
-    record[L::lanes + 0] = w[0];
-    record[L::lanes + 1] = w[1];
-    record[L::lanes + 2] = w[2];
+    for (int k = 0; k < L::lanes; k++) r[k] = x[k];
+    r[L::lanes + 0] = w[0];
+    r[L::lanes + 1] = w[1];
+    r[L::lanes + 2] = w[2];
+    if (W % 2 == 0) {
+        float2* out = reinterpret_cast<float2*>(record);
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) out[k] = make_float2(r[2 * k], r[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) record[k] = r[k];
+    }
 }
 
 template<typename Pt>

@@ -545,12 +545,14 @@ public:
         }();
         (void)loaded;
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        dom_mark(-1);
         for (int stage = 0; stage < 2; stage++) {
             Pt* X_stage = stage == 0 ? d_X : d_X1;
             Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
             dom_round(stage, X_stage);
             yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(
                 d_ctl, X_stage, d_old_v, dom.inboxes(stage), n_max, d_n);
+            dom_mark(2);
             cudaEvent_t sweep_start = nullptr, sweep_stop = nullptr;
             if (profiling) {
                 YB_CUDA(cudaEventCreate(&sweep_start));
@@ -563,10 +565,12 @@ public:
                 YB_CUDA(cudaEventRecord(sweep_stop, stream));
                 sweep_events.emplace_back(sweep_start, sweep_stop);
             }
+            dom_mark(3);
             const unsigned epoch = ++dom.drift_epoch;
             yb::dd_allreduce_drift<<<1, yb::DD_MAX_RANKS, 0, stream>>>(d_ctl,
                 stage, dom.mailboxes, dom.my_mailbox(), dom.rank, dom.world,
                 static_cast<int>(epoch & 1u), epoch);
+            dom_mark(4);
             if (stage == 0)
                 yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n,
                     n_max, dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{},
@@ -574,6 +578,7 @@ public:
             else
                 yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                     d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+            dom_mark(5);
         }
         // migration: cells that crossed a face change owner; the others are
         // re-stored in the cube order of the last force evaluation
@@ -582,11 +587,33 @@ public:
             reinterpret_cast<const float3*>(d_dX), dom.inboxes(2), n_max, d_X,
             d_old_v, dom.new_count);
         yb::slab_commit_count<<<1, 1, 0, stream>>>(d_ctl, dom.new_count, d_n);
+        dom_mark(2);
         YB_CUDA(cudaGetLastError());
     }
 
-    // Fill this brick with its share of a seeded, jittered FCC ball.
-    void dom_seed_lattice_ball(
+    // Extension: where a decomposed step spends its time, by CUDA events on the
+    // stream while profile_sweeps is on. Milliseconds since the last read for
+    // {select (pack + remote stores), wait (for the neighbours' flags), unpack,
+    // forces (grid build + sweep), drift sum, update}.
+    static constexpr int DOM_PHASES = 6;
+    void read_dom_profile(float* ms6)
+    {
+        YB_CUDA(cudaStreamSynchronize(stream));
+        for (int q = 0; q < DOM_PHASES; q++) ms6[q] = 0.f;
+        for (size_t k = 1; k < dom_marks.size(); k++) {
+            if (dom_marks[k].second < 0) continue;  // start of a step
+            float ms = 0.f;
+            YB_CUDA(cudaEventElapsedTime(
+                &ms, dom_marks[k - 1].first, dom_marks[k].first));
+            ms6[dom_marks[k].second] += ms;
+        }
+        for (auto& mark : dom_marks) cudaEventDestroy(mark.first);
+        dom_marks.clear();
+    }
+
+    // Fill this brick with its share of a seeded, jittered FCC ball. Returns the
+    // number of cells the share has; if that exceeds n_max, only n_max are kept.
+    int dom_seed_lattice_ball(
         float radius, float dist_to_nb, float jitter, unsigned long long seed)
     {
         assert(dom.active);
@@ -598,9 +625,13 @@ public:
         yb::dd_seed_lattice_ball<Pt><<<yb::sm_count() * 16, 256, 0, stream>>>(
             radius, dist_to_nb, jitter, seed, dom.region, half, n_sites, n_max,
             d_X, d_old_v, d_n);
-        const int n = get_d_n();
-        assert(n <= n_max);
+        YB_CUDA(cudaMemcpyAsync(
+            h_n_pinned, d_n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        YB_CUDA(cudaStreamSynchronize(stream));
+        const int wanted = *h_n_pinned;
+        const int n = wanted < n_max ? wanted : n_max;
         dd_set_counts(n, n);
+        return wanted;
     }
 
 private:
@@ -616,9 +647,20 @@ private:
             dom.n_tiles,
             migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr,
             d_n, n_max, epoch);
+        dom_mark(0);
         if (dom.region.n_peers > 0)
             yb::dd_wait<<<1, 32, 0, stream>>>(d_ctl, dom.inboxes(what), epoch);
+        dom_mark(1);
     }
+    void dom_mark(int phase)
+    {
+        if (!profiling) return;
+        cudaEvent_t event;
+        YB_CUDA(cudaEventCreate(&event));
+        YB_CUDA(cudaEventRecord(event, stream));
+        dom_marks.emplace_back(event, phase);
+    }
+    std::vector<std::pair<cudaEvent_t, int>> dom_marks;
 
 public:
     // Extension: time the pairwise sweep kernels with CUDA events on the

@@ -73,10 +73,27 @@ def build_upstream_tests():
         return list(pool.map(compile_one, UPSTREAM_TESTS))
 
 
+def build_grid_ab():
+    """scripts/grid_build_ab.cu against both header sets (the sort A/B)."""
+    source = os.path.join(ROOT, "scripts", "grid_build_ab.cu")
+    out_dir = os.path.join(ROOT, "tests", "_bin")
+    os.makedirs(out_dir, exist_ok=True)
+    built = []
+    variants = [("grid_ab_product", os.path.join(ROOT, "include"))]
+    if have_reference():
+        variants.append(("grid_ab_reference", os.path.join(REFERENCE, "include")))
+    for name, include in variants:
+        out = os.path.join(out_dir, name)
+        if not _newer(out, [include, source]):
+            _run(["nvcc"] + NVCC_FLAGS + ["-I", include, "-o", out, source])
+        built.append(out)
+    return built
+
+
 def build_checkers():
-    with ThreadPoolExecutor(max_workers=3) as pool:
+    with ThreadPoolExecutor(max_workers=4) as pool:
         jobs = [pool.submit(build_oracle), pool.submit(build_reference),
-                pool.submit(build_upstream_tests)]
+                pool.submit(build_upstream_tests), pool.submit(build_grid_ab)]
         return [job.result() for job in jobs]
 
 

@@ -1069,6 +1069,10 @@ int yb_dom_step(yb_sim*, float, int)
 {
     return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
 }
+int yb_dom_read_profile(yb_sim*, float*)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
 int yb_ipc_export(const void*, unsigned char*)
 {
     return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");

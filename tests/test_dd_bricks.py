@@ -123,7 +123,7 @@ def test_seeded_lattice_ball_is_the_same_tissue_however_it_is_cut(product):
     for bricks in ((1, 1, 1), (1, 2, 2)):
         world = bricks[0] * bricks[1] * bricks[2]
         cuts = dd.ball_brick_cuts(radius, bricks)
-        domains = [dd.BrickDomain(product, "relu_grid", 60_000, gs, 1.0, bricks, cuts,
+        domains = [dd.BrickDomain(product, "relu_grid", 120_000, gs, 1.0, bricks, cuts,
                                   rank, world, face_capacity=60_000)
                    for rank in range(world)]
         streams = [torch.cuda.Stream() for _ in domains]
@@ -139,6 +139,13 @@ def test_seeded_lattice_ball_is_the_same_tissue_however_it_is_cut(product):
         tissues.append(cells[np.lexsort(cells.T[::-1])])
     assert tissues[0].shape == tissues[1].shape
     assert np.array_equal(tissues[0], tissues[1])
+    # a brick that cannot hold its share says so
+    small = dd.BrickDomain(product, "relu_grid", 1000, gs, 1.0, (1, 1, 1),
+                           dd.ball_brick_cuts(radius, (1, 1, 1)), 0, 1, 1000)
+    dd.connect_local([small])
+    with pytest.raises(Exception, match="too small"):
+        small.seed_lattice_ball(radius, d, seed=7)
+    small.close()
     # density of an FCC lattice with nearest-neighbour distance d
     expected = np.sqrt(2.0) / d ** 3 * 4.0 / 3.0 * np.pi * radius ** 3
     assert abs(len(tissues[0]) - expected) < 0.02 * expected

@@ -110,6 +110,7 @@ SIGNATURES = {
                                                 ctypes.c_float, ctypes.c_float,
                                                 ctypes.c_ulonglong, _c_int_p]),
     "yb_dom_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_int]),
+    "yb_dom_read_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "yb_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "yb_ipc_import": (ctypes.c_int, [ctypes.c_void_p,
                                      ctypes.POINTER(ctypes.c_void_p)]),
@@ -436,6 +437,15 @@ class Sim:
     def dom_step(self, dt, n_steps=1):
         self.lib.check(self.lib.cdll.yb_dom_step(self.handle, dt, n_steps),
                        "dom_step")
+
+    def dom_read_profile(self):
+        """-> dict of device milliseconds per phase of the decomposed steps
+        taken since the last read (while profile_sweeps is on)."""
+        ms = np.zeros(6, dtype=np.float32)
+        self.lib.check(self.lib.cdll.yb_dom_read_profile(
+            self.handle, ms.ctypes.data), "dom_read_profile")
+        names = ("select", "wait", "unpack", "forces", "drift_sum", "update")
+        return {name: float(value) for name, value in zip(names, ms)}
 
     def profile_sweeps(self, enable=True):
         self.lib.check(self.lib.cdll.yb_sim_profile_sweeps(

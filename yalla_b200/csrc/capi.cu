@@ -166,6 +166,10 @@ struct yb_sim {
     {
         return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
     }
+    virtual int dom_read_profile(float*)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
     virtual int profile_sweeps(int enable)
     {
         return fail(YB_ENOSYS, "sweep profiling needs the product library");
@@ -607,10 +611,18 @@ struct Sim_base : yb_sim {
         unsigned long long seed, int* n_out) override
     {
         if (!cells.dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
-        cells.dom_seed_lattice_ball(radius, dist_to_nb, jitter, seed);
-        int problems = 0;
-        cells.slab_counts(n_out, nullptr, &problems);
+        const int wanted =
+            cells.dom_seed_lattice_ball(radius, dist_to_nb, jitter, seed);
+        if (n_out) *n_out = wanted;
+        if (wanted > cells.n_max)
+            return fail(YB_EINVAL, "n_max is too small for this brick: it holds " +
+                                       std::to_string(wanted) + " cells");
         return check_cuda("yb_dom_seed_lattice_ball");
+    }
+    int dom_read_profile(float* ms6) override
+    {
+        cells.read_dom_profile(ms6);
+        return check_cuda("yb_dom_read_profile");
     }
     template<Pairwise_interaction<Pt> force, Pairwise_friction<Pt> friction>
     int dom_step_with(float dt, int n_steps)
@@ -1516,6 +1528,11 @@ int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
 int yb_dom_step(yb_sim* sim, float dt, int n_steps)
 {
     return sim->dom_step(dt, n_steps);
+}
+
+int yb_dom_read_profile(yb_sim* sim, float* ms6)
+{
+    return sim->dom_read_profile(ms6);
 }
 
 int yb_ipc_export(const void* d_base, unsigned char* handle64)
