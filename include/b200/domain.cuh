@@ -16,12 +16,15 @@
 //   [inboxes: per (neighbour, round kind) a header and `capacity` records]
 //
 // Round kinds: 0 / 1 = halo of the predictor / corrector stage, 2 = migration.
-// A round of rank A towards neighbour B is ONE kernel, dd_select: a stable
-// single-pass stream compaction (decoupled look-back per destination) that
-// stores the selected records straight into B's inbox over NVLink, and whose
-// last CTA -- after a system-scope fence -- stores the round's epoch into B's
-// flag word. B's stream meanwhile sits in dd_wait until its flags show the
-// epoch, then dd_append_ghosts / dd_merge read the inboxes. An inbox is
+// A round of rank A is two kernels: dd_select, a stable single-pass stream
+// compaction (decoupled look-back per destination) that packs the selected
+// records into A's local outboxes, and dd_push, which streams every outbox
+// into the neighbour's inbox with coalesced 16-byte stores over NVLink (packing
+// straight into peer memory was measured first: record-sized scattered remote
+// stores run at ~35 GB/s and stall the compaction) and whose last CTA -- after
+// a system-scope fence -- stores the round's epoch into the neighbours' flag
+// words. B's stream meanwhile sits in dd_wait until its flags show the epoch,
+// then dd_append_ghosts / dd_merge read the inboxes. An inbox is
 // written again one step later; by then its owner has consumed it, because the
 // writer had to receive two later rounds from that owner first.
 //
@@ -146,6 +149,25 @@ __device__ __forceinline__ unsigned dd_destinations(
     return mask;
 }
 
+// The same from the face flags a previous kernel left for the cell (halo rounds).
+__device__ __forceinline__ unsigned dd_destinations_of_flags(
+    unsigned flags, const Dd_region& region)
+{
+    if (flags == 0) return 0;
+    unsigned mask = 0;
+    for (int p = 0; p < region.n_peers; p++) {
+        bool takes = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const int d = region.dir[p][a];
+            if (d < 0) takes = takes && ((flags >> (2 * a)) & 1u);
+            if (d > 0) takes = takes && ((flags >> (2 * a + 1)) & 1u);
+        }
+        mask |= (takes ? 1u : 0u) << p;
+    }
+    return mask;
+}
+
 // One round towards all peers. Walks the owned cells (or, in a migration
 // round with `order`, every slot of the cube-ordered pos4 plane of the last
 // force evaluation -- the cells that stay are then re-stored in cube order,
@@ -159,7 +181,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
     Dd_region region, Dd_outboxes to, int migration, Pt* __restrict__ X_tmp,
     float3* __restrict__ v_tmp, int* n_stay, unsigned long long* status,
     int n_tiles, const float4* __restrict__ order,
-    const int* __restrict__ d_n_total, int n_max, unsigned epoch)
+    const int* __restrict__ d_n_total, int n_max,
+    const unsigned char* __restrict__ halo_flags)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
     constexpr int WARPS = SCAN_THREADS / 32;
@@ -183,57 +206,82 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
     const int n_peers = region.n_peers;
     const int n_lists = n_peers + (permute ? 1 : 0);
 
+    // A halo round with face flags at hand: most tiles hold no cell near a face.
+    // Such a tile only takes part in the look-backs (zero aggregates, resolved
+    // to prefixes so that later tiles need not walk far) and is done.
+    bool idle = false;
+    if (halo_flags != nullptr && !permute) {
+        const int base = first + 8 * t;  // 8 consecutive flag bytes per thread
+        unsigned long long word = 0;
+        if (base + 8 <= n) {
+            word = __ldg(reinterpret_cast<const unsigned long long*>(halo_flags + base));
+        } else {
+            for (int k = 0; k < 8; k++)
+                if (base + k < n) word |= halo_flags[base + k];
+        }
+        idle = __syncthreads_or(word != 0) == 0;
+    }
+
     unsigned mask[SELECT_SUB];  // bit p: goes to peer p; bit 31: a ghost entry
     int cell[SELECT_SUB];
+    if (!idle) {
 #pragma unroll
-    for (int u = 0; u < SELECT_SUB; u++) {
-        const int q = first + u * SCAN_THREADS + t;
-        mask[u] = 0;
-        cell[u] = q;
-        if (q < n) {
-            bool ghost = false;
-            if (permute) {
-                cell[u] = __float_as_int(__ldg(&order[q].w));
-                ghost = cell[u] >= n_owned;
+        for (int u = 0; u < SELECT_SUB; u++) {
+            const int q = first + u * SCAN_THREADS + t;
+            mask[u] = 0;
+            cell[u] = q;
+            if (q < n) {
+                bool ghost = false;
+                if (permute) {
+                    cell[u] = __float_as_int(__ldg(&order[q].w));
+                    ghost = cell[u] >= n_owned;
+                }
+                if (ghost) {
+                    mask[u] = 1u << 31;
+                } else if (halo_flags != nullptr) {  // halo round with flags
+                    mask[u] =
+                        dd_destinations_of_flags(__ldg(halo_flags + q), region);
+                } else {
+                    const float* x = reinterpret_cast<const float*>(P + cell[u]);
+                    const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
+                    mask[u] = dd_destinations(pos, region, migration != 0);
+                }
             }
-            if (ghost) {
-                mask[u] = 1u << 31;
-            } else {
-                const float* x = reinterpret_cast<const float*>(P + cell[u]);
-                const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
-                mask[u] = dd_destinations(pos, region, migration != 0);
+            for (int l = 0; l < n_lists; l++) {
+                const unsigned bit =
+                    l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
+                const unsigned votes = __ballot_sync(0xffffffffu, bit);
+                if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
             }
-        }
-        for (int l = 0; l < n_lists; l++) {
-            const unsigned bit = l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
-            const unsigned votes = __ballot_sync(0xffffffffu, bit);
-            if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
         }
     }
     __syncthreads();
     // exclusive scan of the SUB x WARPS counts of every list, one warp per list
     for (int l = warp_id; l < n_lists; l += WARPS) {
-        constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
-        unsigned short* counts = &s_count[l][0][0];
-        int mine[PER_LANE], sum = 0;
+        int aggregate = 0;
+        if (!idle) {
+            constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
+            unsigned short* counts = &s_count[l][0][0];
+            int mine[PER_LANE], sum = 0;
 #pragma unroll
-        for (int q = 0; q < PER_LANE; q++) {
-            mine[q] = counts[lane_id * PER_LANE + q];
-            sum += mine[q];
-        }
-        int incl = sum;
+            for (int q = 0; q < PER_LANE; q++) {
+                mine[q] = counts[lane_id * PER_LANE + q];
+                sum += mine[q];
+            }
+            int incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane_id >= d) incl += up;
-        }
-        int running = incl - sum;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane_id >= d) incl += up;
+            }
+            int running = incl - sum;
 #pragma unroll
-        for (int q = 0; q < PER_LANE; q++) {
-            counts[lane_id * PER_LANE + q] = running;
-            running += mine[q];
+            for (int q = 0; q < PER_LANE; q++) {
+                counts[lane_id * PER_LANE + q] = running;
+                running += mine[q];
+            }
+            aggregate = __shfl_sync(0xffffffffu, incl, 31);
         }
-        const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
         const int exclusive = scan_lookback(
             status + size_t(l) * n_tiles, tile, scan_epoch, aggregate, lane_id);
         if (lane_id == 0) {
@@ -243,31 +291,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
     }
     __syncthreads();
 
+    if (!idle) {
 #pragma unroll
-    for (int u = 0; u < SELECT_SUB; u++) {
-        const int q = first + u * SCAN_THREADS + t;
-        const int i = cell[u];
-        const unsigned below = (1u << lane_id) - 1u;
-        int leavers_before = 0;  // over all peers (migration: one peer per cell)
-        for (int p = 0; p < n_peers; p++) {
-            const unsigned bit = (mask[u] >> p) & 1u;
-            const unsigned votes = __ballot_sync(0xffffffffu, bit);
-            const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
-                           __popc(votes & below);
-            leavers_before += at;
-            if (bit && at < to.capacity[p])
-                write_record(to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
-        }
-        int ghosts_before = 0;
-        if (permute) {
-            const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
-            ghosts_before = s_tile_prefix[n_peers] +
-                            s_count[n_peers][u][warp_id] + __popc(votes & below);
-        }
-        if (migration && q < n && mask[u] == 0) {
-            const int at = q - leavers_before - ghosts_before;
-            store_pt(X_tmp, at, load_pt(P, i));
-            v_tmp[at] = v[i];
+        for (int u = 0; u < SELECT_SUB; u++) {
+            const int q = first + u * SCAN_THREADS + t;
+            const int i = cell[u];
+            const unsigned below = (1u << lane_id) - 1u;
+            int leavers_before = 0;  // over all peers (migration: one per cell)
+            for (int p = 0; p < n_peers; p++) {
+                const unsigned bit = (mask[u] >> p) & 1u;
+                const unsigned votes = __ballot_sync(0xffffffffu, bit);
+                const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
+                               __popc(votes & below);
+                leavers_before += at;
+                if (bit && at < to.capacity[p])
+                    write_record(
+                        to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
+            }
+            int ghosts_before = 0;
+            if (permute) {
+                const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
+                ghosts_before = s_tile_prefix[n_peers] +
+                                s_count[n_peers][u][warp_id] + __popc(votes & below);
+            }
+            if (migration && q < n && mask[u] == 0) {
+                const int at = q - leavers_before - ghosts_before;
+                store_pt(X_tmp, at, load_pt(P, i));
+                v_tmp[at] = v[i];
+            }
         }
     }
 
@@ -286,18 +337,56 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
             leaving += __shfl_xor_sync(0xffffffffu, leaving, d);
         if (migration && t == 0) *n_stay = n_owned - leaving;
     }
-    // Everything this CTA stored in peer memory must be visible system-wide
-    // before the epoch; the last CTA to finish publishes it and re-arms the scan.
-    __threadfence_system();
-    __syncthreads();
+    // The last tile to finish re-arms the control words for the next launch.
     if (t == 0) {
+        __threadfence();
         if (atomicAdd(&scan_ctl->scan_tiles_done, 1) == n_tiles - 1) {
             scan_ctl->scan_next_tile = 0;
             scan_ctl->scan_tiles_done = 0;
             scan_ctl->scan_epoch =
                 static_cast<int>((scan_epoch + 1u) & 0x3fffffffu);
+            __threadfence();
+        }
+    }
+}
+
+// Stream every local outbox (header + the records it holds) into the inbox of
+// its neighbour: a few dozen CTAs per peer, 16-byte loads and stores. After a
+// system-scope fence the last CTA to finish stores the epoch into the peers'
+// flag words.
+inline int dd_push_ctas()
+{
+    static const int ctas = [] {
+        const char* env = getenv("YALLA_B200_PUSH_CTAS");
+        const int wanted = env && env[0] ? atoi(env) : 0;
+        return wanted > 0 ? wanted : 24;
+    }();
+    return ctas;
+}
+
+__global__ void __launch_bounds__(256) dd_push(Dd_outboxes from, Dd_outboxes to,
+    int n_peers, int ctas_per_peer, int record_floats, int* push_done,
+    unsigned epoch)
+{
+    const int DD_PUSH_CTAS = ctas_per_peer;
+    const int p = blockIdx.x / DD_PUSH_CTAS, part = blockIdx.x % DD_PUSH_CTAS;
+    if (p < n_peers) {
+        const int count = __float_as_int(from.buffer[p][0]);
+        // whole float4s, header included (buffers are padded to 256 bytes)
+        const int n_vec = (SLAB_HEADER + count * record_floats + 3) / 4;
+        const float4* src = reinterpret_cast<const float4*>(from.buffer[p]);
+        float4* dst = reinterpret_cast<float4*>(to.buffer[p]);
+        for (int q = part * blockDim.x + threadIdx.x; q < n_vec;
+             q += DD_PUSH_CTAS * blockDim.x)
+            dst[q] = src[q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(push_done, 1) == int(gridDim.x) - 1) {
+            *push_done = 0;
             __threadfence_system();
-            for (int p = 0; p < n_peers; p++) store_release_sys(to.flag[p], epoch);
+            for (int q = 0; q < n_peers; q++) store_release_sys(to.flag[q], epoch);
         }
     }
 }
@@ -356,7 +445,7 @@ template<typename Pt>
 __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
     const int* __restrict__ n_stay_in, const Pt* __restrict__ X_tmp,
     const float3* __restrict__ v_tmp, Dd_inboxes in, int n_max, Pt* X, float3* v,
-    int* new_count)
+    int* new_count, Halo_faces faces, unsigned char* __restrict__ halo_flags)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
     __shared__ int s_start[DD_MAX_PEERS + 1];
@@ -376,6 +465,9 @@ __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
             read_record(in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W, X,
                 v, r);
         }
+        // faces the cell is close to: the first halo round of the next step
+        const float* x = reinterpret_cast<const float*>(X + r);
+        halo_flags[r] = halo_flags_of(x[0], x[1], x[2], faces);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = total;
 }
@@ -484,7 +576,10 @@ struct Domain_link {
     size_t inbox_offset[DD_MAX_PEERS][DD_ROUNDS] = {};
     size_t flag_offset[DD_MAX_PEERS][DD_ROUNDS] = {};
 
-    Dd_outboxes out[DD_ROUNDS] = {};  // filled by connect()
+    Dd_outboxes out[DD_ROUNDS] = {};  // the peers' inboxes, filled by connect()
+    Dd_outboxes local_out{};           // where dd_select packs, per peer
+    unsigned char* local_base = nullptr;
+    int* push_done = nullptr;
     Dd_mailboxes mailboxes{};
     unsigned epoch[DD_ROUNDS] = {0, 0, 0};
     unsigned drift_epoch = 0;
@@ -495,7 +590,19 @@ struct Domain_link {
     Step_ctl* scan_ctl = nullptr;
     int* n_stay = nullptr;
     int* new_count = nullptr;
+    unsigned char* halo_flags = nullptr;  // per owned cell, see Halo_faces
+    bool flags_valid = false;             // false until a kernel has written them
     bool permute = true;
+
+    Halo_faces inset_faces() const
+    {
+        Halo_faces faces;
+        for (int a = 0; a < 3; a++) {
+            faces.lo[a] = region.lo[a] + region.halo;
+            faces.hi[a] = region.hi[a] - region.halo;
+        }
+        return faces;
+    }
 
     static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -534,6 +641,23 @@ struct Domain_link {
         bytes = at;
         YB_CUDA(cudaMalloc(&base, bytes));
         YB_CUDA(cudaMemset(base, 0, bytes));
+        // local outboxes, one per peer (a round is pushed before the next packs)
+        size_t local_bytes = 0;
+        size_t local_offset[DD_MAX_PEERS];
+        for (int p = 0; p < region.n_peers; p++) {
+            local_offset[p] = local_bytes;
+            local_bytes = align_up(local_bytes + sizeof(float) * (SLAB_HEADER +
+                                       size_t(capacity[p]) * record_floats));
+        }
+        YB_CUDA(cudaMalloc(&local_base, local_bytes > 0 ? local_bytes : 256));
+        YB_CUDA(cudaMemset(local_base, 0, local_bytes > 0 ? local_bytes : 256));
+        local_out = Dd_outboxes{};
+        for (int p = 0; p < region.n_peers; p++) {
+            local_out.buffer[p] = reinterpret_cast<float*>(local_base + local_offset[p]);
+            local_out.capacity[p] = capacity[p];
+        }
+        YB_CUDA(cudaMalloc(&push_done, sizeof(int)));
+        YB_CUDA(cudaMemset(push_done, 0, sizeof(int)));
         for (int r = 0; r < DD_MAX_RANKS; r++) mailboxes.of_rank[r] = nullptr;
         mailboxes.of_rank[rank] = reinterpret_cast<Dd_mailbox*>(base);
 
@@ -547,6 +671,8 @@ struct Domain_link {
         YB_CUDA(cudaMemcpy(scan_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
         YB_CUDA(cudaMalloc(&n_stay, sizeof(int)));
         YB_CUDA(cudaMalloc(&new_count, sizeof(int)));
+        YB_CUDA(cudaMalloc(&halo_flags, n_max > 0 ? n_max : 1));
+        flags_valid = false;
         const char* env = getenv("YALLA_B200_SLAB_PERMUTE");
         permute = !(env && env[0] == '0');
         for (int q = 0; q < DD_ROUNDS; q++) epoch[q] = 0;
@@ -606,10 +732,13 @@ struct Domain_link {
     void release()
     {
         if (!active) return;
+        cudaFree(halo_flags);
         cudaFree(new_count);
         cudaFree(n_stay);
         cudaFree(scan_ctl);
         cudaFree(status);
+        cudaFree(push_done);
+        cudaFree(local_base);
         cudaFree(base);
         base = nullptr;
         active = false;

@@ -176,6 +176,24 @@ __device__ __forceinline__ int cube_of(float x, float y, float z,
     return static_cast<int>(id);
 }
 
+// The faces of a brick of a decomposed tissue, moved inwards by the halo width:
+// a cell outside [lo, hi) on an axis is within the halo of that face and has to
+// be copied to the neighbour behind it (b200/domain.cuh). Bit 2a: below lo[a],
+// bit 2a + 1: at or above hi[a].
+struct Halo_faces {
+    float lo[3], hi[3];
+};
+
+__device__ __forceinline__ unsigned char halo_flags_of(
+    float x, float y, float z, const Halo_faces& faces)
+{
+    unsigned flags = 0;
+    flags |= (x < faces.lo[0] ? 1u : 0u) | (x >= faces.hi[0] ? 2u : 0u);
+    flags |= (y < faces.lo[1] ? 4u : 0u) | (y >= faces.hi[1] ? 8u : 0u);
+    flags |= (z < faces.lo[2] ? 16u : 0u) | (z >= faces.hi[2] ? 32u : 0u);
+    return static_cast<unsigned char>(flags);
+}
+
 __device__ __forceinline__ int live_cells(const int* d_n, int n_max)
 {
     const int n = *d_n;

@@ -22,13 +22,17 @@
 namespace yb {
 
 // X1 = X + (dX - drift) * dt, and -- for the grid solver -- the cube id of X1
-// plus its bucket arrival rank (step 1 of the next grid build, fused).
+// plus its bucket arrival rank (step 1 of the next grid build, fused). In a
+// decomposed run (halo_flags != nullptr) also which faces of the brick X1 is
+// close to, so that the halo round of the second stage need not read the
+// positions again.
 template<typename Pt, bool BIN>
 __global__ void __launch_bounds__(256) predictor_step(
     const int* __restrict__ d_n, int n_max, float dt,
     const Pt* __restrict__ d_X, const Pt* __restrict__ d_dX,
     Pt* __restrict__ d_X1, Step_ctl* ctl, float cube_size, Grid_box box,
-    int* __restrict__ key, int* __restrict__ arrival, int* count)
+    int* __restrict__ key, int* __restrict__ arrival, int* count,
+    Halo_faces faces = Halo_faces{}, unsigned char* __restrict__ halo_flags = nullptr)
 {
     const int n = live_cells(d_n, n_max);
     const float fx = ctl->drift[0][0], fy = ctl->drift[0][1],
@@ -41,6 +45,7 @@ __global__ void __launch_bounds__(256) predictor_step(
         dX.z -= fz;
         const Pt X1 = load_pt(d_X, i) + dX * dt;
         store_pt(d_X1, i, X1);
+        if (halo_flags) halo_flags[i] = halo_flags_of(X1.x, X1.y, X1.z, faces);
         if (BIN) {
             const int c = cube_of(
                 X1.x, X1.y, X1.z, cube_size, box, &ctl->out_of_grid);

@@ -430,6 +430,7 @@ public:
     void slab_set_owned(const Pt* d_X_new, const float3* d_v_new, int n_owned)
     {
         assert(n_owned <= n_max);
+        dom.flags_valid = false;
         YB_CUDA(cudaMemcpyAsync(d_X, d_X_new, sizeof(Pt) * size_t(n_owned),
             cudaMemcpyDeviceToDevice, stream));
         YB_CUDA(cudaMemcpyAsync(d_old_v, d_v_new, sizeof(float3) * size_t(n_owned),
@@ -533,6 +534,7 @@ public:
         // or merely late (one process per GPU). Load everything up front.
         static const bool loaded = [] {
             yb::load_kernel(yb::dd_select<Pt>);
+            yb::load_kernel(yb::dd_push);
             yb::load_kernel(yb::dd_wait);
             yb::load_kernel(yb::dd_append_ghosts<Pt>);
             yb::load_kernel(yb::dd_merge<Pt>);
@@ -574,7 +576,7 @@ public:
             if (stage == 0)
                 yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n,
                     n_max, dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{},
-                    nullptr, nullptr, nullptr);
+                    nullptr, nullptr, nullptr, dom.inset_faces(), dom.halo_flags);
             else
                 yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
                     d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
@@ -585,19 +587,21 @@ public:
         dom_round(2, d_X);
         yb::dd_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, dom.n_stay, d_X1,
             reinterpret_cast<const float3*>(d_dX), dom.inboxes(2), n_max, d_X,
-            d_old_v, dom.new_count);
+            d_old_v, dom.new_count, dom.inset_faces(), dom.halo_flags);
         yb::slab_commit_count<<<1, 1, 0, stream>>>(d_ctl, dom.new_count, d_n);
+        dom.flags_valid = true;
         dom_mark(2);
         YB_CUDA(cudaGetLastError());
     }
 
     // Extension: where a decomposed step spends its time, by CUDA events on the
     // stream while profile_sweeps is on. Milliseconds since the last read for
-    // {select (pack + remote stores), wait (for the neighbours' flags), unpack,
-    // forces (grid build + sweep), drift sum, update}.
-    static constexpr int DOM_PHASES = 6;
-    void read_dom_profile(float* ms6)
+    // {select (pack), wait (for the neighbours' flags), unpack, forces (grid
+    // build + sweep), drift sum, update, push (outboxes -> neighbours)}.
+    static constexpr int DOM_PHASES = 7;
+    void read_dom_profile(float* ms7)
     {
+        float* ms6 = ms7;
         YB_CUDA(cudaStreamSynchronize(stream));
         for (int q = 0; q < DOM_PHASES; q++) ms6[q] = 0.f;
         for (size_t k = 1; k < dom_marks.size(); k++) {
@@ -631,6 +635,7 @@ public:
         const int wanted = *h_n_pinned;
         const int n = wanted < n_max ? wanted : n_max;
         dd_set_counts(n, n);
+        dom.flags_valid = false;
         return wanted;
     }
 
@@ -641,16 +646,27 @@ private:
         const bool migration = what == 2;
         const unsigned epoch = ++dom.epoch[what];
         // X1 and dX are free at the end of a step: scratch for the stayers
+        // a brick without neighbours has no halo; its migration round still
+        // re-stores the cells in cube order
+        if (dom.region.n_peers == 0 && !migration) return;
         yb::dd_select<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
-            dom.scan_ctl, P, d_old_v, dom.region, dom.out[what], migration,
+            dom.scan_ctl, P, d_old_v, dom.region, dom.local_out, migration,
             d_X1, reinterpret_cast<float3*>(d_dX), dom.n_stay, dom.status,
             dom.n_tiles,
             migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr,
-            d_n, n_max, epoch);
+            d_n, n_max,
+            // stage 0: flags from the last dd_merge (not before the first
+            // step); stage 1: from the predictor just now
+            (what == 1 || (what == 0 && dom.flags_valid)) ? dom.halo_flags : nullptr);
         dom_mark(0);
-        if (dom.region.n_peers > 0)
+        if (dom.region.n_peers > 0) {
+            yb::dd_push<<<dom.region.n_peers * yb::dd_push_ctas(), 256, 0,
+                stream>>>(dom.local_out, dom.out[what], dom.region.n_peers,
+                yb::dd_push_ctas(), dom.record_floats, dom.push_done, epoch);
+            dom_mark(6);
             yb::dd_wait<<<1, 32, 0, stream>>>(d_ctl, dom.inboxes(what), epoch);
-        dom_mark(1);
+            dom_mark(1);
+        }
     }
     void dom_mark(int phase)
     {

@@ -252,9 +252,10 @@ int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
     float jitter, unsigned long long seed, int* n_out);
 int yb_dom_step(yb_sim* sim, float dt, int n_steps);
 /* While yb_sim_profile_sweeps is on: device milliseconds since the last read
- * spent in {packing + remote stores, waiting for the neighbours' flags,
- * unpacking, grid build + sweep, drift sum, update} (CUDA events). */
-int yb_dom_read_profile(yb_sim* sim, float* ms6);
+ * spent in {packing, waiting for the neighbours' flags, unpacking, grid build +
+ * sweep, drift sum, update, pushing the outboxes to the neighbours} (CUDA
+ * events; 7 floats). */
+int yb_dom_read_profile(yb_sim* sim, float* ms7);
 /* CUDA IPC plumbing for the above: 64-byte handle of a device allocation,
  * mapping of another process's handle, unmapping. */
 int yb_ipc_export(const void* d_base, unsigned char* handle64);

@@ -441,10 +441,11 @@ class Sim:
     def dom_read_profile(self):
         """-> dict of device milliseconds per phase of the decomposed steps
         taken since the last read (while profile_sweeps is on)."""
-        ms = np.zeros(6, dtype=np.float32)
+        ms = np.zeros(7, dtype=np.float32)
         self.lib.check(self.lib.cdll.yb_dom_read_profile(
             self.handle, ms.ctypes.data), "dom_read_profile")
-        names = ("select", "wait", "unpack", "forces", "drift_sum", "update")
+        names = ("select", "wait", "unpack", "forces", "drift_sum", "update",
+                 "push")
         return {name: float(value) for name, value in zip(names, ms)}
 
     def profile_sweeps(self, enable=True):

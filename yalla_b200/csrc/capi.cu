@@ -1530,9 +1530,9 @@ int yb_dom_step(yb_sim* sim, float dt, int n_steps)
     return sim->dom_step(dt, n_steps);
 }
 
-int yb_dom_read_profile(yb_sim* sim, float* ms6)
+int yb_dom_read_profile(yb_sim* sim, float* ms7)
 {
-    return sim->dom_read_profile(ms6);
+    return sim->dom_read_profile(ms7);
 }
 
 int yb_ipc_export(const void* d_base, unsigned char* handle64)
