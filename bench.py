@@ -613,18 +613,40 @@ def main():
     for k in range(e2e_steps + 2):
         sim.step_host(host_in, spec["dt"], 1, check)
     e2e_verified = bool(np.array_equal(check[:n_in], pipelined))
+    # what the host link gives this rank while all ranks copy at once: the same
+    # two transfers per batch, nothing else (bounds e2e from above)
+    up_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    pinned_in = torch.from_numpy(host_in)
+    device_in = torch.empty_like(pinned_in, device="cuda")
+    device_out = torch.zeros((out_cells, lanes), dtype=torch.float32, device="cuda")
+    pinned_out = torch.from_numpy(outs[0])
+    barrier()
+    copy_start = time.perf_counter()
+    for _ in range(10):
+        with torch.cuda.stream(up_stream):
+            device_in.copy_(pinned_in, non_blocking=True)
+        with torch.cuda.stream(down_stream):
+            pinned_out.copy_(device_out, non_blocking=True)
+    up_stream.synchronize()
+    down_stream.synchronize()
+    barrier()
+    copy_seconds = (time.perf_counter() - copy_start) / 10
     cells = n_in * e2e_steps
     if use_dist:
-        t = torch.tensor([seconds, float(cells)], dtype=torch.float64,
-                         device="cuda")
+        t = torch.tensor([seconds, float(cells), copy_seconds],
+                         dtype=torch.float64, device="cuda")
         worst = t.clone()
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        seconds, cells = float(worst[0]), int(t[1])
+        seconds, cells, copy_seconds = float(worst[0]), int(t[1]), float(worst[2])
     e2e = {"value": cells / seconds, "unit": "cell-updates/s",
            "h2d_bytes_per_step": n_in * lanes * 4,
            "d2h_bytes_per_step": out_cells * lanes * 4 + 4,
            "steps": e2e_steps, "matches_unpipelined_run": e2e_verified,
+           # a batch's two copies alone, all ranks at once: e2e cannot beat
+           # n_in / this; it falls with N when the ranks share the host's links
+           "copies_alone_ms_per_batch": copy_seconds * 1e3,
+           "copies_alone_bound": n_in * world / copy_seconds,
            "how": "independent batches pipelined through one model instance: "
                   "2 copy streams + 2 device staging slots, pinned host buffers"}
     sim.close()

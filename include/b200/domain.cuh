@@ -16,9 +16,9 @@
 //   [inboxes: per (neighbour, round kind) a header and `capacity` records]
 //
 // Round kinds: 0 / 1 = halo of the predictor / corrector stage, 2 = migration.
-// A round of rank A is two kernels: dd_select, a stable single-pass stream
-// compaction (decoupled look-back per destination) that packs the selected
-// records into A's local outboxes, and dd_push, which streams every outbox
+// A round of rank A: a stable stream compaction (dd_tile_counts ->
+// dd_tile_offsets -> dd_pack, entry order preserved per destination) packs the
+// selected records into A's local outboxes, and dd_push streams every outbox
 // into the neighbour's inbox with coalesced 16-byte stores over NVLink (packing
 // straight into peer memory was measured first: record-sized scattered remote
 // stores run at ~35 GB/s and stall the compaction) and whose last CTA -- after
@@ -168,37 +168,169 @@ __device__ __forceinline__ unsigned dd_destinations_of_flags(
     return mask;
 }
 
-// One round towards all peers. Walks the owned cells (or, in a migration
-// round with `order`, every slot of the cube-ordered pos4 plane of the last
-// force evaluation -- the cells that stay are then re-stored in cube order,
-// see slab.cuh), ranks every cell in the list of each peer it goes to, and
-// writes the records to their final places in the peers' inboxes.
-// status: (DD_MAX_PEERS + 1) * n_tiles look-back words (last list: ghosts met
-// while walking `order`).
+// One round towards all peers, as three streaming kernels over tiles of
+// SCAN_TILE entries (a first version used ONE kernel with a decoupled look-back
+// chain per destination; with the 7 neighbours of a brick its latency chains
+// made a halo round cost 0.35 ms for 12.5 M cells):
+//
+//   dd_tile_counts   per tile and destination list: how many of its entries go
+//                    there (lists: the peers, plus the ghost entries met when
+//                    a migration round walks the cube-ordered plane);
+//   dd_tile_offsets  exclusive scan of those counts over the tiles, one CTA per
+//                    list; totals -> outbox headers, stayer count, overflow;
+//   dd_pack          every tile ranks its entries inside the tile (ballots and
+//                    one shared-memory scan) and writes the records to their
+//                    final places: a stable compaction, entry order preserved.
+//
+// Entries are the owned cells in index order, or -- in a migration round with
+// `order`, the cube-ordered pos4 plane of the last force evaluation -- every
+// slot of that plane: the cells that stay are then re-stored in cube order (see
+// slab.cuh). Halo rounds read the one-byte face flags a previous kernel left
+// per cell when they are at hand, instead of the positions.
+constexpr int DD_LISTS = DD_MAX_PEERS + 1;
+
 template<typename Pt>
-__global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
-    Step_ctl* scan_ctl, const Pt* __restrict__ P, const float3* __restrict__ v,
-    Dd_region region, Dd_outboxes to, int migration, Pt* __restrict__ X_tmp,
-    float3* __restrict__ v_tmp, int* n_stay, unsigned long long* status,
-    int n_tiles, const float4* __restrict__ order,
+__device__ __forceinline__ void dd_classify(int tile, int t, const Step_ctl* ctl,
+    const Pt* __restrict__ P, const Dd_region& region, bool migration,
+    const float4* __restrict__ order, int n, int n_owned,
+    const unsigned char* __restrict__ halo_flags, unsigned* mask, int* cell)
+{
+    const bool permute = order != nullptr;
+    const int first = tile * SCAN_TILE;
+#pragma unroll
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int q = first + u * SCAN_THREADS + t;
+        mask[u] = 0;
+        cell[u] = q;
+        if (q >= n) continue;
+        bool ghost = false;
+        if (permute) {
+            cell[u] = __float_as_int(__ldg(&order[q].w));
+            ghost = cell[u] >= n_owned;
+        }
+        if (ghost) {
+            mask[u] = 1u << 31;
+        } else if (halo_flags != nullptr) {
+            mask[u] = dd_destinations_of_flags(__ldg(halo_flags + q), region);
+        } else {
+            const float* x = reinterpret_cast<const float*>(P + cell[u]);
+            const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
+            mask[u] = dd_destinations(pos, region, migration);
+        }
+    }
+}
+
+template<typename Pt>
+__global__ void __launch_bounds__(SCAN_THREADS) dd_tile_counts(const Step_ctl* ctl,
+    const Pt* __restrict__ P, Dd_region region, int migration,
+    const float4* __restrict__ order, const int* __restrict__ d_n_total,
+    int n_max, const unsigned char* __restrict__ halo_flags,
+    int* __restrict__ tile_counts, int n_tiles)
+{
+    __shared__ int s_total[DD_LISTS];
+    const int t = threadIdx.x, lane_id = t & 31;
+    const int tile = blockIdx.x;
+    const int n_owned = ctl->n_owned;
+    const bool permute = order != nullptr;
+    const int n = permute ? live_cells(d_n_total, n_max) : n_owned;
+    const int n_lists = region.n_peers + (permute ? 1 : 0);
+    if (t < DD_LISTS) s_total[t] = 0;
+    __syncthreads();
+    if (tile * SCAN_TILE < n) {
+        unsigned mask[SELECT_SUB];
+        int cell[SELECT_SUB];
+        dd_classify(tile, t, ctl, P, region, migration != 0, order, n, n_owned,
+            halo_flags, mask, cell);
+        unsigned any = 0;
+#pragma unroll
+        for (int u = 0; u < SELECT_SUB; u++) any |= mask[u];
+        // most warps of most tiles hold no cell that goes anywhere
+        if (__any_sync(0xffffffffu, any != 0)) {
+            for (int l = 0; l < n_lists; l++) {
+                int mine = 0;
+#pragma unroll
+                for (int u = 0; u < SELECT_SUB; u++)
+                    mine += l < region.n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1)
+                    mine += __shfl_xor_sync(0xffffffffu, mine, d);
+                if (lane_id == 0 && mine > 0) atomicAdd(&s_total[l], mine);
+            }
+        }
+    }
+    __syncthreads();
+    if (t < n_lists) tile_counts[size_t(t) * n_tiles + tile] = s_total[t];
+}
+
+// One CTA per list: tile_counts -> exclusive offsets (in place); the totals go
+// to the outbox headers (peers) and into totals[] (all lists).
+__global__ void __launch_bounds__(1024) dd_tile_offsets(Step_ctl* ctl,
+    int* __restrict__ tile_counts, int n_tiles, Dd_outboxes to, int n_peers,
+    int* __restrict__ totals)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int l = blockIdx.x, t = threadIdx.x;
+    const int lane_id = t & 31, warp_id = t >> 5;
+    int* counts = tile_counts + size_t(l) * n_tiles;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int q = base + t;
+        const int mine = q < n_tiles ? counts[q] : 0;
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_id >= d) incl += up;
+        }
+        if (lane_id == 31) s_warp[warp_id] = incl;
+        __syncthreads();
+        if (warp_id == 0) {
+            int w = s_warp[lane_id];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane_id >= d) w += up;
+            }
+            s_warp[lane_id] = w;  // inclusive over the warps
+        }
+        __syncthreads();
+        const int before = s_carry + (warp_id > 0 ? s_warp[warp_id - 1] : 0);
+        if (q < n_tiles) counts[q] = before + incl - mine;
+        __syncthreads();
+        if (t == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (t == 0) {
+        const int total = s_carry;
+        totals[l] = total;
+        if (l < n_peers) {
+            if (total > to.capacity[l]) atomicAdd(&ctl->out_of_grid, 1 << 20);
+            to.buffer[l][0] = __int_as_float(min(total, to.capacity[l]));
+        }
+    }
+}
+
+template<typename Pt>
+__global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
+    const Pt* __restrict__ P, const float3* __restrict__ v, Dd_region region,
+    Dd_outboxes to, int migration, Pt* __restrict__ X_tmp,
+    float3* __restrict__ v_tmp, int* n_stay, const float4* __restrict__ order,
     const int* __restrict__ d_n_total, int n_max,
-    const unsigned char* __restrict__ halo_flags)
+    const unsigned char* __restrict__ halo_flags,
+    const int* __restrict__ tile_offsets, const int* __restrict__ totals,
+    int n_tiles)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
     constexpr int WARPS = SCAN_THREADS / 32;
-    constexpr int LISTS = DD_MAX_PEERS + 1;
-    __shared__ int s_tile;
-    __shared__ unsigned short s_count[LISTS][SELECT_SUB][WARPS];  // then: prefixes
-    __shared__ int s_total[LISTS];
-    __shared__ int s_tile_prefix[LISTS];
+    __shared__ unsigned short s_count[DD_LISTS][SELECT_SUB][WARPS];  // -> prefixes
+    __shared__ int s_tile_prefix[DD_LISTS];
+    __shared__ int s_busy;
 
     const int t = threadIdx.x;
     const int lane_id = t & 31, warp_id = t >> 5;
-    if (t == 0) s_tile = atomicAdd(&scan_ctl->scan_next_tile, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    const unsigned scan_epoch =
-        static_cast<unsigned>(*(volatile int*)&scan_ctl->scan_epoch) & 0x3fffffffu;
+    const int tile = blockIdx.x;
     const int n_owned = ctl->n_owned;
     const bool permute = order != nullptr;
     const int n = permute ? live_cells(d_n_total, n_max) : n_owned;
@@ -206,146 +338,90 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_select(Step_ctl* ctl,
     const int n_peers = region.n_peers;
     const int n_lists = n_peers + (permute ? 1 : 0);
 
-    // A halo round with face flags at hand: most tiles hold no cell near a face.
-    // Such a tile only takes part in the look-backs (zero aggregates, resolved
-    // to prefixes so that later tiles need not walk far) and is done.
-    bool idle = false;
-    if (halo_flags != nullptr && !permute) {
-        const int base = first + 8 * t;  // 8 consecutive flag bytes per thread
-        unsigned long long word = 0;
-        if (base + 8 <= n) {
-            word = __ldg(reinterpret_cast<const unsigned long long*>(halo_flags + base));
-        } else {
-            for (int k = 0; k < 8; k++)
-                if (base + k < n) word |= halo_flags[base + k];
-        }
-        idle = __syncthreads_or(word != 0) == 0;
+    if (tile == 0 && t == 0 && migration) {
+        int leaving = 0;
+        for (int p = 0; p < n_peers; p++) leaving += totals[p];
+        *n_stay = n_owned - leaving;
     }
+    if (first >= n) return;
+    // what lies in front of this tile in every list; a halo tile whose own
+    // counts are all zero has nothing to do
+    if (t == 0) s_busy = migration;
+    __syncthreads();
+    if (t < n_lists) {
+        const int here = tile_offsets[size_t(t) * n_tiles + tile];
+        s_tile_prefix[t] = here;
+        const int next = tile + 1 < n_tiles
+                             ? tile_offsets[size_t(t) * n_tiles + tile + 1]
+                             : totals[t];
+        if (next != here) s_busy = 1;
+    }
+    __syncthreads();
+    if (!s_busy) return;
 
     unsigned mask[SELECT_SUB];  // bit p: goes to peer p; bit 31: a ghost entry
     int cell[SELECT_SUB];
-    if (!idle) {
+    dd_classify(tile, t, ctl, P, region, migration != 0, order, n, n_owned,
+        halo_flags, mask, cell);
 #pragma unroll
-        for (int u = 0; u < SELECT_SUB; u++) {
-            const int q = first + u * SCAN_THREADS + t;
-            mask[u] = 0;
-            cell[u] = q;
-            if (q < n) {
-                bool ghost = false;
-                if (permute) {
-                    cell[u] = __float_as_int(__ldg(&order[q].w));
-                    ghost = cell[u] >= n_owned;
-                }
-                if (ghost) {
-                    mask[u] = 1u << 31;
-                } else if (halo_flags != nullptr) {  // halo round with flags
-                    mask[u] =
-                        dd_destinations_of_flags(__ldg(halo_flags + q), region);
-                } else {
-                    const float* x = reinterpret_cast<const float*>(P + cell[u]);
-                    const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
-                    mask[u] = dd_destinations(pos, region, migration != 0);
-                }
-            }
-            for (int l = 0; l < n_lists; l++) {
-                const unsigned bit =
-                    l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
-                const unsigned votes = __ballot_sync(0xffffffffu, bit);
-                if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
-            }
+    for (int u = 0; u < SELECT_SUB; u++) {
+        for (int l = 0; l < n_lists; l++) {
+            const unsigned bit = l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
+            const unsigned votes = __ballot_sync(0xffffffffu, bit);
+            if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
         }
     }
     __syncthreads();
     // exclusive scan of the SUB x WARPS counts of every list, one warp per list
     for (int l = warp_id; l < n_lists; l += WARPS) {
-        int aggregate = 0;
-        if (!idle) {
-            constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
-            unsigned short* counts = &s_count[l][0][0];
-            int mine[PER_LANE], sum = 0;
+        constexpr int ENTRIES = SELECT_SUB * WARPS, PER_LANE = ENTRIES / 32;
+        unsigned short* counts = &s_count[l][0][0];
+        int mine[PER_LANE], sum = 0;
 #pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                mine[q] = counts[lane_id * PER_LANE + q];
-                sum += mine[q];
-            }
-            int incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane_id >= d) incl += up;
-            }
-            int running = incl - sum;
-#pragma unroll
-            for (int q = 0; q < PER_LANE; q++) {
-                counts[lane_id * PER_LANE + q] = running;
-                running += mine[q];
-            }
-            aggregate = __shfl_sync(0xffffffffu, incl, 31);
+        for (int q = 0; q < PER_LANE; q++) {
+            mine[q] = counts[lane_id * PER_LANE + q];
+            sum += mine[q];
         }
-        const int exclusive = scan_lookback(
-            status + size_t(l) * n_tiles, tile, scan_epoch, aggregate, lane_id);
-        if (lane_id == 0) {
-            s_total[l] = aggregate;
-            s_tile_prefix[l] = exclusive;
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_id >= d) incl += up;
+        }
+        int running = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            counts[lane_id * PER_LANE + q] = running;
+            running += mine[q];
         }
     }
     __syncthreads();
 
-    if (!idle) {
 #pragma unroll
-        for (int u = 0; u < SELECT_SUB; u++) {
-            const int q = first + u * SCAN_THREADS + t;
-            const int i = cell[u];
-            const unsigned below = (1u << lane_id) - 1u;
-            int leavers_before = 0;  // over all peers (migration: one per cell)
-            for (int p = 0; p < n_peers; p++) {
-                const unsigned bit = (mask[u] >> p) & 1u;
-                const unsigned votes = __ballot_sync(0xffffffffu, bit);
-                const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
-                               __popc(votes & below);
-                leavers_before += at;
-                if (bit && at < to.capacity[p])
-                    write_record(
-                        to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
-            }
-            int ghosts_before = 0;
-            if (permute) {
-                const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
-                ghosts_before = s_tile_prefix[n_peers] +
-                                s_count[n_peers][u][warp_id] + __popc(votes & below);
-            }
-            if (migration && q < n && mask[u] == 0) {
-                const int at = q - leavers_before - ghosts_before;
-                store_pt(X_tmp, at, load_pt(P, i));
-                v_tmp[at] = v[i];
-            }
+    for (int u = 0; u < SELECT_SUB; u++) {
+        const int q = first + u * SCAN_THREADS + t;
+        const int i = cell[u];
+        const unsigned below = (1u << lane_id) - 1u;
+        int leavers_before = 0;  // over all peers (migration: one per cell)
+        for (int p = 0; p < n_peers; p++) {
+            const unsigned bit = (mask[u] >> p) & 1u;
+            const unsigned votes = __ballot_sync(0xffffffffu, bit);
+            const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
+                           __popc(votes & below);
+            leavers_before += at;
+            if (bit && at < to.capacity[p])
+                write_record(to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
         }
-    }
-
-    // the tile that holds the last entry knows the totals
-    const int last_tile = n > 0 ? (n - 1) / SCAN_TILE : 0;
-    if (tile == last_tile && t < 32) {
-        int leaving = 0;
-        for (int p = t; p < n_peers; p += 32) {
-            const int total = s_tile_prefix[p] + s_total[p];
-            if (total > to.capacity[p]) atomicAdd(&ctl->out_of_grid, 1 << 20);
-            to.buffer[p][0] = __int_as_float(min(total, to.capacity[p]));
-            leaving += total;
+        int ghosts_before = 0;
+        if (permute) {
+            const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
+            ghosts_before = s_tile_prefix[n_peers] +
+                            s_count[n_peers][u][warp_id] + __popc(votes & below);
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1)
-            leaving += __shfl_xor_sync(0xffffffffu, leaving, d);
-        if (migration && t == 0) *n_stay = n_owned - leaving;
-    }
-    // The last tile to finish re-arms the control words for the next launch.
-    if (t == 0) {
-        __threadfence();
-        if (atomicAdd(&scan_ctl->scan_tiles_done, 1) == n_tiles - 1) {
-            scan_ctl->scan_next_tile = 0;
-            scan_ctl->scan_tiles_done = 0;
-            scan_ctl->scan_epoch =
-                static_cast<int>((scan_epoch + 1u) & 0x3fffffffu);
-            __threadfence();
+        if (migration && q < n && mask[u] == 0) {
+            const int at = q - leavers_before - ghosts_before;
+            store_pt(X_tmp, at, load_pt(P, i));
+            v_tmp[at] = v[i];
         }
     }
 }
@@ -584,10 +660,10 @@ struct Domain_link {
     unsigned epoch[DD_ROUNDS] = {0, 0, 0};
     unsigned drift_epoch = 0;
 
-    // scratch of dd_select
+    // scratch of the compaction: per list and tile, counts then offsets
     int n_tiles = 0;
-    unsigned long long* status = nullptr;
-    Step_ctl* scan_ctl = nullptr;
+    int* tile_counts = nullptr;
+    int* totals = nullptr;
     int* n_stay = nullptr;
     int* new_count = nullptr;
     unsigned char* halo_flags = nullptr;  // per owned cell, see Halo_faces
@@ -662,13 +738,11 @@ struct Domain_link {
         mailboxes.of_rank[rank] = reinterpret_cast<Dd_mailbox*>(base);
 
         n_tiles = ceil_div(n_max > 0 ? n_max : 1, SCAN_TILE);
-        const size_t words = size_t(DD_MAX_PEERS + 1) * n_tiles;
-        YB_CUDA(cudaMalloc(&status, words * sizeof(unsigned long long)));
-        YB_CUDA(cudaMemset(status, 0, words * sizeof(unsigned long long)));
-        YB_CUDA(cudaMalloc(&scan_ctl, sizeof(Step_ctl)));
-        Step_ctl fresh{};
-        fresh.scan_epoch = 1;
-        YB_CUDA(cudaMemcpy(scan_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
+        const size_t words = size_t(DD_LISTS) * n_tiles;
+        YB_CUDA(cudaMalloc(&tile_counts, words * sizeof(int)));
+        YB_CUDA(cudaMemset(tile_counts, 0, words * sizeof(int)));
+        YB_CUDA(cudaMalloc(&totals, DD_LISTS * sizeof(int)));
+        YB_CUDA(cudaMemset(totals, 0, DD_LISTS * sizeof(int)));
         YB_CUDA(cudaMalloc(&n_stay, sizeof(int)));
         YB_CUDA(cudaMalloc(&new_count, sizeof(int)));
         YB_CUDA(cudaMalloc(&halo_flags, n_max > 0 ? n_max : 1));
@@ -735,8 +809,8 @@ struct Domain_link {
         cudaFree(halo_flags);
         cudaFree(new_count);
         cudaFree(n_stay);
-        cudaFree(scan_ctl);
-        cudaFree(status);
+        cudaFree(totals);
+        cudaFree(tile_counts);
         cudaFree(push_done);
         cudaFree(local_base);
         cudaFree(base);

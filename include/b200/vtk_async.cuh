@@ -34,7 +34,9 @@
 #include <vector>
 
 #include "../cudebug.cuh"
+#include "../links.cuh"
 #include "../polarity.cuh"
+#include "../property.cuh"
 #include "grid_build.cuh"
 
 template<typename Pt, template<typename> class Solver>
@@ -96,10 +98,15 @@ public:
         for (auto& slot : slots) {
             cudaFree(slot.d_cells);
             cudaFree(slot.d_count);
+            cudaFree(slot.d_links);
+            cudaFree(slot.d_link_count);
+            for (auto* values : slot.d_properties) cudaFree(values);
             cudaEventDestroy(slot.ready);
         }
         cudaFreeHost(h_cells);
         cudaFreeHost(h_count);
+        cudaFreeHost(h_links);
+        for (auto& property : properties) cudaFreeHost(property.h_values);
         cudaStreamDestroy(copy_stream);
     }
 
@@ -113,6 +120,40 @@ public:
         const char* data_name = "polarity")
     {
         polarities.push_back({data_name, lane_of(theta), lane_of(phi)});
+    }
+
+    // Links as a LINES section behind the vertices, like Vtk_output::write_links;
+    // per-cell properties (int, enum or float) as SCALARS behind the fields and
+    // polarities, like Vtk_output::write_property. Both are snapshotted on the
+    // device together with the cells (the links with their own device-side
+    // count). Register before the first write().
+    void add_links(Links& links_to_write)
+    {
+        assert(next_frame == 0 && links == nullptr);
+        links = &links_to_write;
+        const size_t n_links = static_cast<size_t>(links->n_max > 0 ? links->n_max : 1);
+        for (auto& slot : slots) {
+            YB_CUDA(cudaMalloc(&slot.d_links, n_links * sizeof(Link)));
+            YB_CUDA(cudaMalloc(&slot.d_link_count, sizeof(int)));
+        }
+        YB_CUDA(cudaMallocHost(&h_links, n_links * sizeof(Link) + sizeof(int)));
+    }
+    template<typename Prop>
+    void add_property(Property<Prop>& property)
+    {
+        static_assert(sizeof(Prop) == 4, "int, enum or float properties");
+        assert(next_frame == 0 && property.n_max >= n_max);
+        Property_field field;
+        field.name = property.name;
+        field.is_float = std::is_same<Prop, float>::value;
+        field.d_source = reinterpret_cast<const uint32_t*>(property.d_prop);
+        YB_CUDA(cudaMallocHost(&field.h_values, static_cast<size_t>(n_max) * 4));
+        properties.push_back(field);
+        for (auto& slot : slots) {
+            uint32_t* values;
+            YB_CUDA(cudaMalloc(&values, static_cast<size_t>(n_max) * 4));
+            slot.d_properties.push_back(values);
+        }
     }
 
     // Snapshot the state as it is in stream order and queue the frame.
@@ -133,6 +174,16 @@ public:
             256, 0, points.stream>>>(points.d_n, points.n_max, words,
             reinterpret_cast<const uint32_t*>(points.d_X),
             reinterpret_cast<uint32_t*>(slot->d_cells), slot->d_count);
+        if (links != nullptr)
+            yb::snapshot_cells<<<yb::stride_grid(links->n_max * 2, 256,
+                                     yb::sm_count()),
+                256, 0, points.stream>>>(links->d_n, links->n_max, 2,
+                reinterpret_cast<const uint32_t*>(links->d_link),
+                reinterpret_cast<uint32_t*>(slot->d_links), slot->d_link_count);
+        for (size_t k = 0; k < properties.size(); k++)
+            yb::snapshot_cells<<<yb::stride_grid(points.n_max, 256, yb::sm_count()),
+                256, 0, points.stream>>>(points.d_n, points.n_max, 1,
+                properties[k].d_source, slot->d_properties[k], slot->d_count);
         YB_CUDA(cudaEventRecord(slot->ready, points.stream));
         slot->frame = next_frame++;
         {
@@ -164,8 +215,17 @@ private:
     struct Slot {
         Pt* d_cells = nullptr;
         int* d_count = nullptr;
+        Link* d_links = nullptr;
+        int* d_link_count = nullptr;
+        std::vector<uint32_t*> d_properties;
         cudaEvent_t ready = nullptr;
         int frame = 0;
+    };
+    struct Property_field {
+        std::string name;
+        bool is_float = false;
+        const uint32_t* d_source = nullptr;
+        uint32_t* h_values = nullptr;  // pinned
     };
     struct Field {
         std::string name;
@@ -203,6 +263,21 @@ private:
             YB_CUDA(cudaMemcpyAsync(h_cells, slot->d_cells,
                 static_cast<size_t>(n) * sizeof(Pt), cudaMemcpyDeviceToHost,
                 copy_stream));
+            int n_links = 0;
+            if (links != nullptr) {
+                int* h_link_count = reinterpret_cast<int*>(h_links + links->n_max);
+                YB_CUDA(cudaMemcpyAsync(h_link_count, slot->d_link_count,
+                    sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+                YB_CUDA(cudaStreamSynchronize(copy_stream));
+                n_links = *h_link_count;
+                YB_CUDA(cudaMemcpyAsync(h_links, slot->d_links,
+                    static_cast<size_t>(n_links) * sizeof(Link),
+                    cudaMemcpyDeviceToHost, copy_stream));
+            }
+            for (size_t k = 0; k < properties.size(); k++)
+                YB_CUDA(cudaMemcpyAsync(properties[k].h_values,
+                    slot->d_properties[k], static_cast<size_t>(n) * 4,
+                    cudaMemcpyDeviceToHost, copy_stream));
             YB_CUDA(cudaStreamSynchronize(copy_stream));
             const int frame = slot->frame;
             {
@@ -212,7 +287,7 @@ private:
                 free_slots.push_back(slot);
             }
             // (wait() must not see all slots free before the file is written)
-            write_frame(frame, n);
+            write_frame(frame, n, n_links);
             {
                 std::lock_guard<std::mutex> lock(mutex);
                 in_flight--;
@@ -246,7 +321,7 @@ private:
         out.clear();
     }
 
-    void write_frame(int frame, int n)
+    void write_frame(int frame, int n, int n_links)
     {
         std::ofstream file(frame_path(frame), std::ios::binary);
         assert(file.is_open());
@@ -282,7 +357,23 @@ private:
             for (int i = 0; i < n; i++) file << "1 " << i << "\n";
         }
 
-        if (!fields.empty() || !polarities.empty())
+        if (links != nullptr) {
+            file << "\nLINES " << n_links << " " << 3 * n_links << "\n";
+            if (binary) {
+                for (int i = 0; i < n_links; i++) {
+                    out.push_back(yb::big_endian(2u));
+                    out.push_back(yb::big_endian(static_cast<uint32_t>(h_links[i].a)));
+                    out.push_back(yb::big_endian(static_cast<uint32_t>(h_links[i].b)));
+                }
+                flush(file, out);
+                file << "\n";
+            } else {
+                for (int i = 0; i < n_links; i++)
+                    file << "2 " << h_links[i].a << " " << h_links[i].b << "\n";
+            }
+        }
+
+        if (!fields.empty() || !polarities.empty() || !properties.empty())
             file << "\nPOINT_DATA " << n << "\n";
         for (const auto& field : fields) {
             file << "SCALARS " << field.name << " float\n"
@@ -310,6 +401,26 @@ private:
                 file << "\n";
             }
         }
+        for (const auto& property : properties) {
+            file << "SCALARS " << property.name << " "
+                 << (property.is_float ? "float" : "int") << "\n"
+                 << "LOOKUP_TABLE default\n";
+            if (binary) {
+                for (int i = 0; i < n; i++)
+                    out.push_back(yb::big_endian(property.h_values[i]));
+                flush(file, out);
+                file << "\n";
+            } else if (property.is_float) {
+                for (int i = 0; i < n; i++) {
+                    float v;
+                    memcpy(&v, &property.h_values[i], sizeof(v));
+                    file << v << "\n";
+                }
+            } else {
+                for (int i = 0; i < n; i++)
+                    file << static_cast<int>(property.h_values[i]) << "\n";
+            }
+        }
     }
 
     const int n_max;
@@ -318,6 +429,9 @@ private:
     std::vector<Slot> slots;
     std::vector<Field> fields;
     std::vector<Polarity_field> polarities;
+    std::vector<Property_field> properties;
+    Links* links = nullptr;
+    Link* h_links = nullptr;  // pinned, followed by the count
     Pt* h_cells = nullptr;
     int* h_count = nullptr;
     cudaStream_t copy_stream = nullptr;

@@ -533,7 +533,9 @@ public:
         // kernels this very thread has yet to enqueue (bricks sharing a process)
         // or merely late (one process per GPU). Load everything up front.
         static const bool loaded = [] {
-            yb::load_kernel(yb::dd_select<Pt>);
+            yb::load_kernel(yb::dd_tile_counts<Pt>);
+            yb::load_kernel(yb::dd_tile_offsets);
+            yb::load_kernel(yb::dd_pack<Pt>);
             yb::load_kernel(yb::dd_push);
             yb::load_kernel(yb::dd_wait);
             yb::load_kernel(yb::dd_append_ghosts<Pt>);
@@ -596,12 +598,13 @@ public:
 
     // Extension: where a decomposed step spends its time, by CUDA events on the
     // stream while profile_sweeps is on. Milliseconds since the last read for
-    // {select (pack), wait (for the neighbours' flags), unpack, forces (grid
-    // build + sweep), drift sum, update, push (outboxes -> neighbours)}.
-    static constexpr int DOM_PHASES = 7;
-    void read_dom_profile(float* ms7)
+    // {select (packing the two halo rounds), wait (for the neighbours' flags),
+    // unpack, forces (grid build + sweep), drift sum, update, push (outboxes ->
+    // neighbours), migration select (with the re-store in cube order)}.
+    static constexpr int DOM_PHASES = 8;
+    void read_dom_profile(float* ms8)
     {
-        float* ms6 = ms7;
+        float* ms6 = ms8;
         YB_CUDA(cudaStreamSynchronize(stream));
         for (int q = 0; q < DOM_PHASES; q++) ms6[q] = 0.f;
         for (size_t k = 1; k < dom_marks.size(); k++) {
@@ -649,16 +652,25 @@ private:
         // a brick without neighbours has no halo; its migration round still
         // re-stores the cells in cube order
         if (dom.region.n_peers == 0 && !migration) return;
-        yb::dd_select<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
-            dom.scan_ctl, P, d_old_v, dom.region, dom.local_out, migration,
-            d_X1, reinterpret_cast<float3*>(d_dX), dom.n_stay, dom.status,
-            dom.n_tiles,
-            migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr,
-            d_n, n_max,
-            // stage 0: flags from the last dd_merge (not before the first
-            // step); stage 1: from the predictor just now
-            (what == 1 || (what == 0 && dom.flags_valid)) ? dom.halo_flags : nullptr);
-        dom_mark(0);
+        const float4* order =
+            migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr;
+        // stage 0: flags from the last dd_merge (not before the first step);
+        // stage 1: from the predictor just now
+        const unsigned char* flags =
+            (what == 1 || (what == 0 && dom.flags_valid)) ? dom.halo_flags : nullptr;
+        const int n_lists = dom.region.n_peers + (order != nullptr ? 1 : 0);
+        yb::dd_tile_counts<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
+            P, dom.region, migration, order, d_n, n_max, flags, dom.tile_counts,
+            dom.n_tiles);
+        if (n_lists > 0)
+            yb::dd_tile_offsets<<<n_lists, 1024, 0, stream>>>(d_ctl,
+                dom.tile_counts, dom.n_tiles, dom.local_out, dom.region.n_peers,
+                dom.totals);
+        yb::dd_pack<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl, P,
+            d_old_v, dom.region, dom.local_out, migration, d_X1,
+            reinterpret_cast<float3*>(d_dX), dom.n_stay, order, d_n, n_max, flags,
+            dom.tile_counts, dom.totals, dom.n_tiles);
+        dom_mark(migration ? 7 : 0);
         if (dom.region.n_peers > 0) {
             yb::dd_push<<<dom.region.n_peers * yb::dd_push_ctas(), 256, 0,
                 stream>>>(dom.local_out, dom.out[what], dom.region.n_peers,

@@ -314,6 +314,8 @@ inline void Vtk_input::index_binary_sections()
             payload = size_t(n_points) * 3 * sizeof(float);
         } else if (items[0] == "VERTICES") {
             payload = size_t(stoi(items[1])) * 2 * sizeof(uint32_t);
+        } else if (items[0] == "LINES" && items.size() > 2) {
+            payload = size_t(stoi(items[2])) * sizeof(uint32_t);
         } else if (items[0] == "SCALARS") {
             getline(file, line);  // LOOKUP_TABLE default
             payload = size_t(n_points) * sizeof(float);

@@ -57,6 +57,8 @@ const char* yb_last_error(void);
  *  "spring_grid"  float3 (3)  Grid    the same, Grid_solver
  *  "relu_tile"    float3 (3)  Tile    include/inits.cuh:78-93 relu_force
  *  "relu_grid"    float3 (3)  Grid    the same, Grid_solver
+ *  "relu_gabriel" float3 (3)  Gabriel the same, Gabriel_solver (solvers.cuh:
+ *                                     505-644; GPU libraries only)
  *  "epithelium"   Po_cell (5) Grid    examples/epithelium.cu:16-31 layer_force,
  *                                     friction_on_background
  *  "growth"       Po_cell (5) Grid    examples/passive_growth.cu: relu_w_epithelium
@@ -252,10 +254,11 @@ int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
     float jitter, unsigned long long seed, int* n_out);
 int yb_dom_step(yb_sim* sim, float dt, int n_steps);
 /* While yb_sim_profile_sweeps is on: device milliseconds since the last read
- * spent in {packing, waiting for the neighbours' flags, unpacking, grid build +
- * sweep, drift sum, update, pushing the outboxes to the neighbours} (CUDA
- * events; 7 floats). */
-int yb_dom_read_profile(yb_sim* sim, float* ms7);
+ * spent in {packing the halo rounds, waiting for the neighbours' flags,
+ * unpacking, grid build + sweep, drift sum, update, pushing the outboxes to the
+ * neighbours, the migration round's packing and re-store} (CUDA events; 8
+ * floats). */
+int yb_dom_read_profile(yb_sim* sim, float* ms8);
 /* CUDA IPC plumbing for the above: 64-byte handle of a device allocation,
  * mapping of another process's handle, unmapping. */
 int yb_ipc_export(const void* d_base, unsigned char* handle64);

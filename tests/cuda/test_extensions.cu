@@ -17,6 +17,7 @@
 #include "../../include/solvers.cuh"
 #include "../../include/vtk.cuh"
 #include "../../include/b200/division.cuh"
+#include "../../include/b200/protrusions.cuh"
 
 #define CHECK(cond, name)                                   \
     do {                                                    \
@@ -125,6 +126,66 @@ static void check_division()
     }
 }
 
+// ---- Protrusion_update: rewiring as a library operation ---------------------------
+// rule: take a partner if there is none yet, or if it is closer than the current
+__device__ bool closer_partner(
+    const float3* __restrict__ d_X, int a, int b, Link current, float noise)
+{
+    if (current.a == current.b) return true;
+    const float3 now = d_X[current.a] - d_X[current.b];
+    const float3 then = d_X[a] - d_X[b];
+    return norm3df(then.x, then.y, then.z) < norm3df(now.x, now.y, now.z);
+}
+
+static void check_protrusions()
+{
+    const int n = 30000, n_max = 40000, prots = 2;
+    const float r_protrusion = 2.f;
+    std::vector<Link> first_run;
+    for (int run = 0; run < 2; run++) {
+        Solution<float3, Grid_solver> cells{n_max, 64, 1.f};
+        *cells.h_n = n;
+        for (int i = 0; i < n_max; i++) cells.h_X[i] = float3{0};
+        cells.copy_to_device();
+        seeded_sphere(0.8f, cells, 5);
+        Links protrusions{n_max * prots, 0.2f};
+        Protrusion_update<float3> update{n_max, prots, 77, 40};
+        for (int round = 0; round < 4; round++)
+            update.rewire<closer_partner>(cells, protrusions, r_protrusion);
+        cudaDeviceSynchronize();
+        protrusions.copy_to_host();
+        cells.copy_to_host();
+        if (run == 0) {
+            CHECK(*protrusions.h_n == n * prots, "the links' count follows the cells'");
+            int live = 0;
+            bool sane = true;
+            for (int l = 0; l < n * prots; l++) {
+                const Link link = protrusions.h_link[l];
+                if (link.a == link.b) continue;
+                live++;
+                sane = sane && link.a == l / prots && link.b >= 0 && link.b < n;
+                if (!sane) break;
+                const float3 r = cells.h_X[link.a] - cells.h_X[link.b];
+                sane = sane && sqrtf(r.x * r.x + r.y * r.y + r.z * r.z) <=
+                                   r_protrusion * (1 + 1e-6f);
+            }
+            CHECK(sane, "links belong to their cell and span at most r_protrusion");
+            CHECK(live > n * prots / 4, "most cells found partners in four rounds");
+            first_run.assign(protrusions.h_link, protrusions.h_link + n * prots);
+            // pulled through link_forces inside a step: action = reaction
+            cells.take_step<relu_force<float3>>(0.05f,
+                [&](const int, const float3* d_X, float3* d_dX) {
+                    link_forces(protrusions, d_X, d_dX);
+                });
+            CHECK(cudaDeviceSynchronize() == cudaSuccess, "step with rewired links");
+        } else {
+            CHECK(memcmp(first_run.data(), protrusions.h_link,
+                      sizeof(Link) * n * prots) == 0,
+                "rewiring is reproducible bit for bit");
+        }
+    }
+}
+
 int main(int argc, char** argv)
 {
     const std::string dir = argc > 1 ? argv[1] : "/tmp/yb_ext_test/";
@@ -206,6 +267,50 @@ int main(int argc, char** argv)
         CHECK(close, "binary and ASCII frames read back the same state");
     }
 
+    // ---- links and properties in the frame ---------------------------------
+    {
+        Links protrusions{n_max, 0.2f};
+        Property<int> kind{n_max, "kind"};
+        Property<float> weight{n_max, "weight"};
+        for (int i = 0; i < n_max; i++) {
+            protrusions.h_link[i] = Link{i, (i * 7 + 1) % n};
+            kind.h_prop[i] = i % 3;
+            weight.h_prop[i] = 0.25f * (i % 9);
+        }
+        *protrusions.h_n = n / 2;
+        protrusions.copy_to_device();
+        kind.copy_to_device();
+        weight.copy_to_device();
+        Vtk_output sync_out{"linked", dir + "sync/", false};
+        Vtk_async_output<Po_cell> async_out{n_max, "linked", dir + "async/", false};
+        async_out.add_links(protrusions);
+        async_out.add_polarity(&Po_cell::theta, &Po_cell::phi);
+        async_out.add_property(kind);
+        async_out.add_property(weight);
+        Vtk_async_output<Po_cell> binary_out{n_max, "linked_binary", dir, true};
+        binary_out.add_links(protrusions);
+        binary_out.add_property(kind);
+        async_out.write(cells);
+        binary_out.write(cells);
+        cells.copy_to_host();
+        sync_out.write_positions(cells);
+        sync_out.write_links(protrusions);
+        sync_out.write_polarity(cells);
+        sync_out.write_property(kind);
+        sync_out.write_property(weight);
+        async_out.wait();
+        binary_out.wait();
+        const std::string a = slurp(dir + "sync/linked_0.vtk");
+        CHECK(!a.empty() && a == slurp(async_out.frame_path(0)),
+            "async frame with links and properties identical to Vtk_output");
+        Vtk_input binary_in{binary_out.frame_path(0)};
+        Property<int> kind_back{n_max, "kind"};
+        binary_in.read_property(kind_back, "kind");
+        bool same = true;
+        for (int i = 0; i < n; i++) same = same && kind_back.h_prop[i] == kind.h_prop[i];
+        CHECK(same, "binary frame with links: the property reads back");
+    }
+
     // ---- a growing tissue: the frame holds the device-side count -----------
     {
         Vtk_async_output<Po_cell> out{n_max, "grown", dir, false};
@@ -256,6 +361,7 @@ int main(int argc, char** argv)
     }
 
     check_division();
+    check_protrusions();
     printf("all extension checks passed\n");
     return 0;
 }

@@ -162,6 +162,18 @@ def test_model_vs_reference_library(product, reference, model, n, lanes, dt, ste
         assert np.array_equal(got["epi_nbs"], want["epi_nbs"])
 
 
+def test_gabriel_solver_vs_reference_library(product, reference):
+    # Gabriel_solver (reference solvers.cuh:505-644): neighbours within the
+    # cut-off whose Gabriel sphere holds no third cell
+    n, steps = 20000, 5
+    X = workloads.lattice_ball(n, 0.8, np.random.default_rng(33))
+    case = dict(model="relu_gabriel", X=X, dt=0.1, steps=steps,
+                grid_size=workloads.grid_size_for(n, 0.8), params={}, types=None,
+                links=None)
+    got, want = run_case(product, case), run_case(reference, case)
+    assert_states_close(got["X_out"], want["X_out"], steps, "gabriel")
+
+
 def test_tile_and_grid_agree(product):
     # tests/test_solvers.cu:102-125 of the reference
     X = workloads.random_ball(50, 0.733333, np.random.default_rng(6))

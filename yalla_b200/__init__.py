@@ -142,11 +142,11 @@ SIGNATURES = {
 
 MODEL_LANES = {
     "springs": 3, "spring_tile": 3, "spring_grid": 3, "relu_tile": 3,
-    "relu_grid": 3, "protrusions": 3, "epithelium": 5, "growth": 5,
+    "relu_grid": 3, "relu_gabriel": 3, "protrusions": 3, "epithelium": 5, "growth": 5,
     "branching": 7, "branching_growth": 7,
 }
-# models that draw from curand: no CPU oracle
-GPU_ONLY_MODELS = {"branching_growth"}
+# models without a CPU oracle (curand; the Gabriel solver)
+GPU_ONLY_MODELS = {"branching_growth", "relu_gabriel"}
 
 
 class YallaError(RuntimeError):
@@ -441,11 +441,11 @@ class Sim:
     def dom_read_profile(self):
         """-> dict of device milliseconds per phase of the decomposed steps
         taken since the last read (while profile_sweeps is on)."""
-        ms = np.zeros(7, dtype=np.float32)
+        ms = np.zeros(8, dtype=np.float32)
         self.lib.check(self.lib.cdll.yb_dom_read_profile(
             self.handle, ms.ctypes.data), "dom_read_profile")
-        names = ("select", "wait", "unpack", "forces", "drift_sum", "update",
-                 "push")
+        names = ("select_halo", "wait", "unpack", "forces", "drift_sum", "update",
+                 "push", "select_migration")
         return {name: float(value) for name, value in zip(names, ms)}
 
     def profile_sweeps(self, enable=True):

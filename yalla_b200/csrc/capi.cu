@@ -1301,6 +1301,9 @@ int yb_sim_create(const char* model, int n_max, int grid_size, float cube_size,
     else if (name == "relu_grid")
         sim = new Spring_sim<Grid_solver, relu_force<float3>>(
             n_max, grid_size, cube_size);
+    else if (name == "relu_gabriel")
+        sim = new Spring_sim<Gabriel_solver, relu_force<float3>>(
+            n_max, grid_size, cube_size);
     else if (name == "protrusions")
         sim = new Protrusion_sim(n_max, grid_size, cube_size);
     else if (name == "epithelium")
@@ -1530,9 +1533,9 @@ int yb_dom_step(yb_sim* sim, float dt, int n_steps)
     return sim->dom_step(dt, n_steps);
 }
 
-int yb_dom_read_profile(yb_sim* sim, float* ms7)
+int yb_dom_read_profile(yb_sim* sim, float* ms8)
 {
-    return sim->dom_read_profile(ms7);
+    return sim->dom_read_profile(ms8);
 }
 
 int yb_ipc_export(const void* d_base, unsigned char* handle64)
