@@ -224,13 +224,16 @@ def pair_statistics(X, cube_size=1.0, sample=200_000):
 
 
 def sweep_traffic(workload):
-    """DRAM bytes per sweep_cubes launch from the committed `ncu --set full`
-    capture of this workload (profiles/r01_sweep_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
-    if not os.path.exists(path):
-        return None
-    entry = json.load(open(path)).get(workload)
-    return None if entry is None else entry["dram_bytes_per_launch"]
+    """DRAM bytes per sweep (sweep_cubes, or list_cubes + interact_lists) from
+    the committed `ncu --set full` captures of this workload
+    (profiles/r02_sweep_traffic.json, else round 1's), or None."""
+    for name in ("r02_sweep_traffic.json", "r01_sweep_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            entry = json.load(open(path)).get(workload)
+            if entry is not None:
+                return entry["dram_bytes_per_launch"]
+    return None
 
 
 def cpu_baseline(spec, steps=10, sample_cells=1_000_000):
@@ -690,7 +693,9 @@ def main():
                 "fp32_lane_instr_per_s_T"]
         fp32_achieved = per_cell * cells_per_launch / (avg_ms * 1e-3) / 1e12
         roofline = {
-            "bound": "fp32_issue", "kernel": "sweep_cubes",
+            "bound": "fp32_issue",
+            "kernel": "sweep_cubes" if lanes <= 4 else
+            "list_cubes + interact_lists (the sweep of points with extra lanes)",
             "achieved": fp32_achieved, "peak": fp32_peak,
             "unit": "T lane-instr/s", "frac": fp32_achieved / fp32_peak,
             "peak_kind": "microbenchmark (profiles/r01_microbench_peaks.json)",

@@ -189,11 +189,50 @@ __device__ __forceinline__ unsigned dd_destinations_of_flags(
 // per cell when they are at hand, instead of the positions.
 constexpr int DD_LISTS = DD_MAX_PEERS + 1;
 
+// Destinations by face code (bit 2a: below the face of axis a, bit 2a + 1: at or
+// above the opposite one): the peers that get a copy (halo round) or the one
+// that takes the cell over (migration round). Filled once per CTA, so that the
+// per-cell work is one table look-up instead of a loop over the peers.
+__device__ __forceinline__ void dd_fill_destinations(
+    unsigned* s_dest, const Dd_region& region, bool migration)
+{
+    const int code = threadIdx.x;
+    if (code >= 64) return;
+    unsigned mask = 0;
+    for (int p = 0; p < region.n_peers; p++) {
+        bool takes = true;
+        for (int a = 0; a < 3; a++) {
+            const int d = region.dir[p][a];
+            const bool below = (code >> (2 * a)) & 1, above = (code >> (2 * a + 1)) & 1;
+            if (d < 0) takes = takes && below;
+            if (d > 0) takes = takes && above;
+            if (d == 0 && migration) takes = takes && !below && !above;
+        }
+        mask |= (takes ? 1u : 0u) << p;
+    }
+    s_dest[code] = mask;
+}
+
+__device__ __forceinline__ unsigned dd_face_code(
+    const float* x, const Dd_region& region, bool migration)
+{
+    const float inset = migration ? 0.f : region.halo;
+    unsigned code = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        code |= (x[a] < region.lo[a] + inset ? 1u : 0u) << (2 * a);
+        code |= (x[a] >= region.hi[a] - inset ? 1u : 0u) << (2 * a + 1);
+    }
+    return code;
+}
+
+// bit p: the entry goes to peer p; bit 31: a ghost entry of the walked plane
 template<typename Pt>
-__device__ __forceinline__ void dd_classify(int tile, int t, const Step_ctl* ctl,
+__device__ __forceinline__ void dd_classify(int tile, int t,
     const Pt* __restrict__ P, const Dd_region& region, bool migration,
     const float4* __restrict__ order, int n, int n_owned,
-    const unsigned char* __restrict__ halo_flags, unsigned* mask, int* cell)
+    const unsigned char* __restrict__ halo_flags, const unsigned* s_dest,
+    unsigned* mask, int* cell)
 {
     const bool permute = order != nullptr;
     const int first = tile * SCAN_TILE;
@@ -211,13 +250,21 @@ __device__ __forceinline__ void dd_classify(int tile, int t, const Step_ctl* ctl
         if (ghost) {
             mask[u] = 1u << 31;
         } else if (halo_flags != nullptr) {
-            mask[u] = dd_destinations_of_flags(__ldg(halo_flags + q), region);
+            const unsigned code = __ldg(halo_flags + q);
+            mask[u] = code ? s_dest[code] : 0u;
         } else {
             const float* x = reinterpret_cast<const float*>(P + cell[u]);
             const float pos[3] = {__ldg(x), __ldg(x + 1), __ldg(x + 2)};
-            mask[u] = dd_destinations(pos, region, migration);
+            const unsigned code = dd_face_code(pos, region, migration);
+            mask[u] = code ? s_dest[code] : 0u;
         }
     }
+}
+
+// list index of a mask bit
+__device__ __forceinline__ int dd_list_of_bit(int bit, int n_peers)
+{
+    return bit == 31 ? n_peers : bit;
 }
 
 template<typename Pt>
@@ -228,6 +275,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_tile_counts(const Step_ctl* c
     int* __restrict__ tile_counts, int n_tiles)
 {
     __shared__ int s_total[DD_LISTS];
+    __shared__ unsigned s_dest[64];
     const int t = threadIdx.x, lane_id = t & 31;
     const int tile = blockIdx.x;
     const int n_owned = ctl->n_owned;
@@ -235,27 +283,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_tile_counts(const Step_ctl* c
     const int n = permute ? live_cells(d_n_total, n_max) : n_owned;
     const int n_lists = region.n_peers + (permute ? 1 : 0);
     if (t < DD_LISTS) s_total[t] = 0;
+    dd_fill_destinations(s_dest, region, migration != 0);
     __syncthreads();
     if (tile * SCAN_TILE < n) {
         unsigned mask[SELECT_SUB];
         int cell[SELECT_SUB];
-        dd_classify(tile, t, ctl, P, region, migration != 0, order, n, n_owned,
-            halo_flags, mask, cell);
+        dd_classify(tile, t, P, region, migration != 0, order, n, n_owned,
+            halo_flags, s_dest, mask, cell);
         unsigned any = 0;
 #pragma unroll
         for (int u = 0; u < SELECT_SUB; u++) any |= mask[u];
-        // most warps of most tiles hold no cell that goes anywhere
-        if (__any_sync(0xffffffffu, any != 0)) {
-            for (int l = 0; l < n_lists; l++) {
-                int mine = 0;
+        // lists some lane of this warp contributes to (most warps: none)
+        unsigned present = __reduce_or_sync(0xffffffffu, any);
+        while (present) {
+            const int bit = __ffs(present) - 1;
+            present &= present - 1;
+            int mine = 0;
 #pragma unroll
-                for (int u = 0; u < SELECT_SUB; u++)
-                    mine += l < region.n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1)
-                    mine += __shfl_xor_sync(0xffffffffu, mine, d);
-                if (lane_id == 0 && mine > 0) atomicAdd(&s_total[l], mine);
-            }
+            for (int u = 0; u < SELECT_SUB; u++) mine += (mask[u] >> bit) & 1u;
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if (lane_id == 0)
+                atomicAdd(&s_total[dd_list_of_bit(bit, region.n_peers)], mine);
         }
     }
     __syncthreads();
@@ -326,6 +374,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
     constexpr int WARPS = SCAN_THREADS / 32;
     __shared__ unsigned short s_count[DD_LISTS][SELECT_SUB][WARPS];  // -> prefixes
     __shared__ int s_tile_prefix[DD_LISTS];
+    __shared__ unsigned s_dest[64];
+    __shared__ float* s_buffer[DD_MAX_PEERS];
+    __shared__ int s_capacity[DD_MAX_PEERS];
     __shared__ int s_busy;
 
     const int t = threadIdx.x;
@@ -356,20 +407,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
                              : totals[t];
         if (next != here) s_busy = 1;
     }
+    if (t < n_peers) {
+        s_buffer[t] = to.buffer[t];
+        s_capacity[t] = to.capacity[t];
+    }
+    dd_fill_destinations(s_dest, region, migration != 0);
     __syncthreads();
     if (!s_busy) return;
 
-    unsigned mask[SELECT_SUB];  // bit p: goes to peer p; bit 31: a ghost entry
+    unsigned mask[SELECT_SUB];
     int cell[SELECT_SUB];
-    dd_classify(tile, t, ctl, P, region, migration != 0, order, n, n_owned,
-        halo_flags, mask, cell);
+    dd_classify(tile, t, P, region, migration != 0, order, n, n_owned, halo_flags,
+        s_dest, mask, cell);
+    // per (sub-block, warp): how many entries go to every list -- lane l keeps
+    // the count of list l; only the lists present in the warp are voted on
 #pragma unroll
     for (int u = 0; u < SELECT_SUB; u++) {
-        for (int l = 0; l < n_lists; l++) {
-            const unsigned bit = l < n_peers ? (mask[u] >> l) & 1u : mask[u] >> 31;
-            const unsigned votes = __ballot_sync(0xffffffffu, bit);
-            if (lane_id == 0) s_count[l][u][warp_id] = __popc(votes);
+        unsigned present = __reduce_or_sync(0xffffffffu, mask[u]);
+        int my_count = 0;
+        while (present) {
+            const int bit = __ffs(present) - 1;
+            present &= present - 1;
+            const unsigned votes = __ballot_sync(0xffffffffu, (mask[u] >> bit) & 1u);
+            if (lane_id == dd_list_of_bit(bit, n_peers)) my_count = __popc(votes);
         }
+        if (lane_id < n_lists) s_count[lane_id][u][warp_id] = my_count;
     }
     __syncthreads();
     // exclusive scan of the SUB x WARPS counts of every list, one warp per list
@@ -397,29 +459,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
     }
     __syncthreads();
 
+    const unsigned below = (1u << lane_id) - 1u;
 #pragma unroll
     for (int u = 0; u < SELECT_SUB; u++) {
         const int q = first + u * SCAN_THREADS + t;
         const int i = cell[u];
-        const unsigned below = (1u << lane_id) - 1u;
-        int leavers_before = 0;  // over all peers (migration: one per cell)
-        for (int p = 0; p < n_peers; p++) {
-            const unsigned bit = (mask[u] >> p) & 1u;
-            const unsigned votes = __ballot_sync(0xffffffffu, bit);
-            const int at = s_tile_prefix[p] + s_count[p][u][warp_id] +
-                           __popc(votes & below);
-            leavers_before += at;
-            if (bit && at < to.capacity[p])
-                write_record(to.buffer[p] + SLAB_HEADER + size_t(at) * W, P, v, i);
+        // entries in front of this warp's row that leave (all peers) / are ghosts
+        int before = 0;
+        if (migration) {
+            before = lane_id < n_lists
+                         ? s_tile_prefix[lane_id] + s_count[lane_id][u][warp_id]
+                         : 0;
+            before = __reduce_add_sync(0xffffffffu, before);
         }
-        int ghosts_before = 0;
-        if (permute) {
-            const unsigned votes = __ballot_sync(0xffffffffu, mask[u] >> 31);
-            ghosts_before = s_tile_prefix[n_peers] +
-                            s_count[n_peers][u][warp_id] + __popc(votes & below);
+        unsigned present = __reduce_or_sync(0xffffffffu, mask[u]);
+        while (present) {
+            const int bit = __ffs(present) - 1;
+            present &= present - 1;
+            const unsigned mine = (mask[u] >> bit) & 1u;
+            const unsigned votes = __ballot_sync(0xffffffffu, mine);
+            const int rank = __popc(votes & below);
+            before += rank;  // (a migrating entry has exactly one bit)
+            if (bit < 31 && mine) {
+                const int at = s_tile_prefix[bit] + s_count[bit][u][warp_id] + rank;
+                if (at < s_capacity[bit])
+                    write_record(
+                        s_buffer[bit] + SLAB_HEADER + size_t(at) * W, P, v, i);
+            }
         }
         if (migration && q < n && mask[u] == 0) {
-            const int at = q - leavers_before - ghosts_before;
+            const int at = q - before;
             store_pt(X_tmp, at, load_pt(P, i));
             v_tmp[at] = v[i];
         }
