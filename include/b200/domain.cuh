@@ -363,12 +363,12 @@ __global__ void __launch_bounds__(1024) dd_tile_offsets(Step_ctl* ctl,
 template<typename Pt>
 __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
     const Pt* __restrict__ P, const float3* __restrict__ v, Dd_region region,
-    Dd_outboxes to, int migration, Pt* __restrict__ X_tmp,
-    float3* __restrict__ v_tmp, int* n_stay, const float4* __restrict__ order,
+    Dd_outboxes to, int migration, Pt* __restrict__ X_stay,
+    float3* __restrict__ v_stay, int* n_stay, const float4* __restrict__ order,
     const int* __restrict__ d_n_total, int n_max,
     const unsigned char* __restrict__ halo_flags,
     const int* __restrict__ tile_offsets, const int* __restrict__ totals,
-    int n_tiles)
+    int n_tiles, Halo_faces faces, unsigned char* __restrict__ flags_stay)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
     constexpr int WARPS = SCAN_THREADS / 32;
@@ -488,9 +488,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
             }
         }
         if (migration && q < n && mask[u] == 0) {
+            // a cell that stays: to its place among the stayers, with the face
+            // flags the first halo round of the next step will read
             const int at = q - before;
-            store_pt(X_tmp, at, load_pt(P, i));
-            v_tmp[at] = v[i];
+            const Pt X = load_pt(P, i);
+            store_pt(X_stay, at, X);
+            v_stay[at] = v[i];
+            flags_stay[at] = halo_flags_of(X.x, X.y, X.z, faces);
         }
     }
 }
@@ -585,11 +589,11 @@ __global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
     }
 }
 
-// Migration, step 2: owned cells := stayers, then the arrivals peer by peer.
+// Migration, step 2: the arrivals, peer by peer, behind the cells that stayed
+// (dd_pack has put those in place already).
 template<typename Pt>
 __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
-    const int* __restrict__ n_stay_in, const Pt* __restrict__ X_tmp,
-    const float3* __restrict__ v_tmp, Dd_inboxes in, int n_max, Pt* X, float3* v,
+    const int* __restrict__ n_stay_in, Dd_inboxes in, int n_max, Pt* X, float3* v,
     int* new_count, Halo_faces faces, unsigned char* __restrict__ halo_flags)
 {
     constexpr int W = Layout<Pt>::lanes + 3;
@@ -597,24 +601,17 @@ __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
     const int n_stay = *n_stay_in;
     if (threadIdx.x == 0) dd_inbox_layout(in, n_max - n_stay, s_start);
     __syncthreads();
-    const int total = n_stay + s_start[in.n_peers];
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total;
-         r += gridDim.x * blockDim.x) {
-        if (r < n_stay) {
-            store_pt(X, r, load_pt(X_tmp, r));
-            v[r] = v_tmp[r];
-        } else {
-            const int a = r - n_stay;
-            int p = 0;
-            while (a >= s_start[p + 1]) p++;
-            read_record(in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W, X,
-                v, r);
-        }
-        // faces the cell is close to: the first halo round of the next step
+    const int arrivals = s_start[in.n_peers];
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < arrivals;
+         a += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (a >= s_start[p + 1]) p++;
+        const int r = n_stay + a;
+        read_record(in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W, X, v, r);
         const float* x = reinterpret_cast<const float*>(X + r);
         halo_flags[r] = halo_flags_of(x[0], x[1], x[2], faces);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = n_stay + arrivals;
 }
 
 // Global drift of a stage: publish {sum dX, n} of the owned cells to every
@@ -736,6 +733,7 @@ struct Domain_link {
     int* n_stay = nullptr;
     int* new_count = nullptr;
     unsigned char* halo_flags = nullptr;  // per owned cell, see Halo_faces
+    float3* v_new = nullptr;  // the corrector's velocities, until re-stored
     bool flags_valid = false;             // false until a kernel has written them
     bool permute = true;
 
@@ -815,6 +813,7 @@ struct Domain_link {
         YB_CUDA(cudaMalloc(&n_stay, sizeof(int)));
         YB_CUDA(cudaMalloc(&new_count, sizeof(int)));
         YB_CUDA(cudaMalloc(&halo_flags, n_max > 0 ? n_max : 1));
+        YB_CUDA(cudaMalloc(&v_new, sizeof(float3) * size_t(n_max > 0 ? n_max : 1)));
         flags_valid = false;
         const char* env = getenv("YALLA_B200_SLAB_PERMUTE");
         permute = !(env && env[0] == '0');
@@ -875,6 +874,7 @@ struct Domain_link {
     void release()
     {
         if (!active) return;
+        cudaFree(v_new);
         cudaFree(halo_flags);
         cudaFree(new_count);
         cudaFree(n_stay);

@@ -55,11 +55,14 @@ __global__ void __launch_bounds__(256) predictor_step(
     }
 }
 
+// X_out / v_out: where the new state goes if not in place (a decomposed run
+// hands it straight to the migration pass, which re-stores it in d_X).
 template<typename Pt>
 __global__ void __launch_bounds__(256) corrector_step(
     const int* __restrict__ d_n, int n_max, float dt,
     const Pt* __restrict__ d_dX, const Pt* __restrict__ d_dX1, Pt* d_X,
-    float3* __restrict__ d_old_v, const Step_ctl* __restrict__ ctl)
+    float3* __restrict__ d_old_v, const Step_ctl* __restrict__ ctl,
+    Pt* X_out = nullptr, float3* v_out = nullptr)
 {
     const int n = live_cells(d_n, n_max);
     const float fx0 = ctl->drift[0][0], fy0 = ctl->drift[0][1],
@@ -79,9 +82,9 @@ __global__ void __launch_bounds__(256) corrector_step(
 
         Pt X = load_pt_rw(d_X, i);
         X += (dX + dX1) * 0.5 * dt;
-        store_pt(d_X, i, X);
+        store_pt(X_out ? X_out : d_X, i, X);
 
-        float* v = reinterpret_cast<float*>(d_old_v + i);
+        float* v = reinterpret_cast<float*>((v_out ? v_out : d_old_v) + i);
         v[0] = (dX.x + dX1.x) * 0.5;
         v[1] = (dX.y + dX1.y) * 0.5;
         v[2] = (dX.z + dX1.z) * 0.5;

@@ -553,7 +553,7 @@ public:
         for (int stage = 0; stage < 2; stage++) {
             Pt* X_stage = stage == 0 ? d_X : d_X1;
             Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
-            dom_round(stage, X_stage);
+            dom_round(stage, X_stage, d_old_v);
             yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(
                 d_ctl, X_stage, d_old_v, dom.inboxes(stage), n_max, d_n);
             dom_mark(2);
@@ -579,17 +579,18 @@ public:
                 yb::predictor_step<Pt, false><<<blocks, 256, 0, stream>>>(d_n,
                     n_max, dt, d_X, d_dX, d_X1, d_ctl, 1.f, yb::Grid_box{},
                     nullptr, nullptr, nullptr, dom.inset_faces(), dom.halo_flags);
-            else
-                yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(
-                    d_n, n_max, dt, d_dX, d_dX1, d_X, d_old_v, d_ctl);
+            else  // the new state goes to X1 / v_new: the migration pass below
+                  // re-stores it in X / old_v in one go
+                yb::corrector_step<Pt><<<blocks, 256, 0, stream>>>(d_n, n_max, dt,
+                    d_dX, d_dX1, d_X, d_old_v, d_ctl, d_X1, dom.v_new);
             dom_mark(5);
         }
         // migration: cells that crossed a face change owner; the others are
         // re-stored in the cube order of the last force evaluation
-        dom_round(2, d_X);
-        yb::dd_merge<Pt><<<blocks, 256, 0, stream>>>(d_ctl, dom.n_stay, d_X1,
-            reinterpret_cast<const float3*>(d_dX), dom.inboxes(2), n_max, d_X,
-            d_old_v, dom.new_count, dom.inset_faces(), dom.halo_flags);
+        dom_round(2, d_X1, dom.v_new);
+        yb::dd_merge<Pt><<<yb::stride_grid(n_max / 16 + 1, 256, yb::sm_count()), 256,
+            0, stream>>>(d_ctl, dom.n_stay, dom.inboxes(2), n_max, d_X, d_old_v,
+            dom.new_count, dom.inset_faces(), dom.halo_flags);
         yb::slab_commit_count<<<1, 1, 0, stream>>>(d_ctl, dom.new_count, d_n);
         dom.flags_valid = true;
         dom_mark(2);
@@ -644,11 +645,12 @@ public:
 
 private:
     // one exchange round: what 0 / 1 = halo of X / X1, 2 = migration
-    void dom_round(int what, const Pt* P)
+    // (cells at P with velocities v; a migration round re-stores the cells that
+    // stay in d_X / d_old_v)
+    void dom_round(int what, const Pt* P, const float3* v)
     {
         const bool migration = what == 2;
         const unsigned epoch = ++dom.epoch[what];
-        // X1 and dX are free at the end of a step: scratch for the stayers
         // a brick without neighbours has no halo; its migration round still
         // re-stores the cells in cube order
         if (dom.region.n_peers == 0 && !migration) return;
@@ -666,10 +668,10 @@ private:
             yb::dd_tile_offsets<<<n_lists, 1024, 0, stream>>>(d_ctl,
                 dom.tile_counts, dom.n_tiles, dom.local_out, dom.region.n_peers,
                 dom.totals);
-        yb::dd_pack<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl, P,
-            d_old_v, dom.region, dom.local_out, migration, d_X1,
-            reinterpret_cast<float3*>(d_dX), dom.n_stay, order, d_n, n_max, flags,
-            dom.tile_counts, dom.totals, dom.n_tiles);
+        yb::dd_pack<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl, P, v,
+            dom.region, dom.local_out, migration, d_X, d_old_v, dom.n_stay, order,
+            d_n, n_max, flags, dom.tile_counts, dom.totals, dom.n_tiles,
+            dom.inset_faces(), dom.halo_flags);
         dom_mark(migration ? 7 : 0);
         if (dom.region.n_peers > 0) {
             yb::dd_push<<<dom.region.n_peers * yb::dd_push_ctas(), 256, 0,
