@@ -1321,15 +1321,19 @@ protected:
     }
 
     // Points with extra lanes run the sweep as two kernels (b200/pair_sweep.cuh,
-    // list_cubes + interact_lists); YALLA_B200_SPLIT_SWEEP=0/1 overrides.
-    static bool split_sweep()
+    // list_cubes + interact_lists) while the cube-ordered planes and the
+    // neighbour lists fit the L2: 1 M-cell tissues gain 2-7 %, but at 10 M cells
+    // the partner gathers and the lists come from HBM and the fused kernel,
+    // which stages positions with bulk copies, is 20 % faster
+    // (profiles/r02_sweep_tuning.md). YALLA_B200_SPLIT_SWEEP=0/1 overrides.
+    bool split_sweep() const
     {
         static const int forced = [] {
             const char* env = getenv("YALLA_B200_SPLIT_SWEEP");
             return env && env[0] ? atoi(env) : -1;
         }();
         if (forced >= 0) return forced != 0;
-        return yb::Layout<Pt>::lanes > 4;
+        return yb::Layout<Pt>::lanes > 4 && n_max <= 4 * 1000 * 1000;
     }
 
     // Cube ids -> bucket sort -> state in cube order (b200/grid_build.cuh).
