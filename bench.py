@@ -305,11 +305,43 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
     n_faces = sum(1 for b in bricks if b > 1) * (2 if max(bricks) > 2 else 1)
     n_max = int(n_target / world * 1.08) + n_faces * int(face_cells * 1.2) + 4096
     lib = yb.product()
-    domain = dd.BrickDomain(lib, spec["model"], n_max, gs, 1.0, bricks, cuts, rank,
-                            world, face_capacity=int(face_cells * 1.3) + 4096)
-    domain.connect_over_ipc()
-    n_seeded = domain.seed_lattice_ball(radius, d, seed=20261017)
-    assert n_seeded <= n_max, (n_seeded, n_max)
+    transport = ("bricks %dx%dx%d, halo exchange + migration + drift sum by kernels "
+                 "over peer memory (NVLink P2P), no NCCL in a step" % bricks)
+    try:
+        domain = dd.BrickDomain(lib, spec["model"], n_max, gs, 1.0, bricks, cuts,
+                                rank, world, face_capacity=int(face_cells * 1.3) + 4096)
+        domain.connect_over_ipc()
+        n_seeded = domain.seed_lattice_ball(radius, d, seed=20261017)
+        assert n_seeded <= n_max, (n_seeded, n_max)
+    except yb.YallaError as error:
+        # no peer mapping between the ranks on this box (raised on every rank):
+        # round 1's transport, z-slabs over torch.distributed send/recv
+        if rank == 0:
+            print(f"bench: {error}; falling back to slabs over NCCL", file=sys.stderr)
+        transport = (f"z-slabs x{world}, halo exchange + migration over NCCL "
+                     "send/recv, drift all-reduce (fallback: no CUDA IPC; tissue "
+                     "generated on the host)")
+        bounds = [-np.inf] + dd.ball_slab_cuts(radius, world) + [np.inf]
+        mine = dd.lattice_ball_slab(radius, d, bounds[rank], bounds[rank + 1],
+                                    np.random.default_rng(1000 + rank))
+        slab_face = int(1.5 * np.pi * radius ** 2 * density)
+        slabs = dd.SlabDomain(lib, spec["model"], int(len(mine) * 1.05) + 2 * slab_face
+                              + 1024, gs, 1.0, bounds[rank], bounds[rank + 1], "cuda",
+                              halo_capacity=slab_face * 13 // 10 + 4096)
+        slabs.set_cells(mine)
+
+        class Stepped:  # the brick driver's interface on the slab driver
+            sim = slabs.sim
+            counts = staticmethod(slabs.counts)
+            owned_state = staticmethod(slabs.owned_state)
+            set_cells = staticmethod(slabs.set_cells)
+            close = staticmethod(slabs.close)
+
+            @staticmethod
+            def step(dt_, n_steps=1):
+                for _ in range(n_steps):
+                    slabs.step(dt_)
+        domain = Stepped
     sampler = ClockSampler(local_rank, 0.05)
     domain.step(dt, warmup)
 
@@ -343,8 +375,11 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
     domain.sim.profile_sweeps(True)
     domain.step(dt, 3)
     sweep_ms, sweep_launches = domain.sim.read_sweep_profile()
-    phases = {name: value / 3 for name, value in
-              domain.sim.dom_read_profile().items()}
+    try:
+        phases = {name: value / 3 for name, value in
+                  domain.sim.dom_read_profile().items()}
+    except yb.YallaError:
+        phases = None
     domain.sim.profile_sweeps(False)
 
     stats = torch.tensor([ms, e2e_seconds, float(n_mine), float(n_out),
@@ -377,9 +412,7 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
         "config": {"workload": workload, "model": spec["model"],
                    "cells_total": cells_total,
                    "cells_per_gpu": cells_total // world, "grid_size": gs,
-                   "dt": dt, "parallelism": "bricks %dx%dx%d, halo exchange + "
-                   "migration + drift sum by kernels over peer memory (NVLink "
-                   "P2P), no NCCL in a step" % bricks,
+                   "dt": dt, "parallelism": transport,
                    "tissue": "jittered FCC ball, seeded on the device",
                    "l2": "working set (>1 GB per rank) exceeds the 126 MB L2"},
         "clocks": clocks,
@@ -713,21 +746,27 @@ def main():
     # the whole 100 M-cell sphere, the T1 of the strong-scaling figure)
     decomposed = None
     if not args.no_decomposed:
-        dd_spec = DD_WORKLOADS["sphere_dd"]
-        dd_steps = max(3, min(steps, 10))
-        record = run_decomposed(dd_steps, 3, dd_spec, "sphere_dd", rank,
-                                local_rank, world, e2e=False)
-        if rank == 0:
-            decomposed = {key: record[key] for key in (
-                "value", "unit", "n_gpus", "steps", "ms_per_step", "ghost_cells",
-                "nvlink_bytes_per_step", "phase_ms_per_step_rank0", "problems",
-                "config")}
-            decomposed["sweep_ms_per_launch"] = record["roofline"]["avg_launch_ms"]
-        if world == 1 and os.environ.get("YALLA_BENCH_STRONG", "1") != "0":
-            whole = run_decomposed(3, 3, dd_spec, "sphere_dd", 0, local_rank, 1,
-                                   cells_total=100_000_000, e2e=False)
-            decomposed["whole_sphere_on_one_gpu"] = {
-                key: whole[key] for key in ("value", "ms_per_step", "steps", "config")}
+        try:
+            dd_spec = DD_WORKLOADS["sphere_dd"]
+            dd_steps = max(3, min(steps, 10))
+            record = run_decomposed(dd_steps, 3, dd_spec, "sphere_dd", rank,
+                                    local_rank, world, e2e=False)
+            if rank == 0:
+                decomposed = {key: record[key] for key in (
+                    "value", "unit", "n_gpus", "steps", "ms_per_step", "ghost_cells",
+                    "nvlink_bytes_per_step", "phase_ms_per_step_rank0", "problems",
+                    "config")}
+                decomposed["sweep_ms_per_launch"] = record["roofline"]["avg_launch_ms"]
+            if world == 1 and os.environ.get("YALLA_BENCH_STRONG", "1") != "0":
+                whole = run_decomposed(3, 3, dd_spec, "sphere_dd", 0, local_rank, 1,
+                                       cells_total=100_000_000, e2e=False)
+                decomposed["whole_sphere_on_one_gpu"] = {
+                    key: whole[key] for key in ("value", "ms_per_step", "steps",
+                                                "config")}
+        except Exception as error:  # the headline line must not depend on it
+            if rank == 0:
+                print(f"bench: decomposed record failed: {error!r}", file=sys.stderr)
+                decomposed = dict(decomposed or {}, error=repr(error))
 
     if rank != 0:
         if use_dist:

@@ -43,6 +43,77 @@ def test_ball_brick_cuts_are_on_cube_boundaries_and_balanced():
     assert np.all(np.abs(share - 0.25) < 0.03)
 
 
+class FakeSim:
+    """Stands in for a library model: records what BrickDomain asks for."""
+    lanes = 3
+
+    def __init__(self):
+        self.begun = None
+        self.connected = {}
+        self.mailboxes = {}
+
+    def dom_begin(self, rank, world, lo, hi, halo, peers, caps, first, count):
+        self.begun = dict(rank=rank, world=world, lo=np.array(lo), hi=np.array(hi),
+                          halo=halo, peers=np.array(peers), caps=np.array(caps),
+                          first=list(first), count=list(count))
+
+    def dom_connect(self, direction, base, offsets6):
+        self.connected[direction] = (base, list(offsets6))
+
+    def dom_connect_mailbox(self, rank, base):
+        self.mailboxes[rank] = base
+
+
+class FakeLib:
+    def sim(self, model, n_max, grid_size, cube_size):
+        return FakeSim()
+
+
+def test_brick_layout_of_a_corner_brick():
+    # rank 5 of 2 x 2 x 2 = brick (1, 0, 1): neighbours towards -x, +y, -z
+    bricks, cuts = (2, 2, 2), [[0.0], [0.0], [0.0]]
+    brick = dd.BrickDomain(FakeLib(), "relu_grid", 1000, 64, 1.0, bricks, cuts, 5, 8,
+                           face_capacity=1600)
+    begun = brick.sim.begun
+    assert brick.coord == (1, 0, 1)
+    assert np.array_equal(begun["lo"], [0, -np.inf, 0])
+    assert np.array_equal(begun["hi"], [np.inf, 0, np.inf])
+    peers = begun["peers"]
+    assert (peers >= 0).sum() == 7 and peers[13] == -1
+    def index(dx, dy, dz):
+        return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)
+    assert peers[index(-1, 0, 0)] == dd.brick_rank((0, 0, 1), bricks)   # face
+    assert peers[index(0, 1, 0)] == dd.brick_rank((1, 1, 1), bricks)
+    assert peers[index(-1, 1, -1)] == dd.brick_rank((0, 1, 0), bricks)  # corner
+    assert peers[index(1, 0, 0)] == -1 and peers[index(0, -1, 0)] == -1
+    caps = begun["caps"]
+    assert caps[index(-1, 0, 0)] == 1600                       # face
+    assert caps[index(-1, 1, 0)] == 1600 // 16 + 2048          # edge
+    assert caps[index(-1, 1, -1)] == 1600 // 256 + 2048        # corner
+    # the box: from the halo (1.5) + 2 cubes of slack below the cut to the grid's end
+    assert begun["first"] == [32 - 4, 0, 32 - 4] and begun["count"] == [36, 36, 36]
+    # connecting: every neighbour's table is read at the OPPOSITE direction
+    bases = list(range(100, 108))
+    tables = [np.arange(27 * 6).reshape(27, 6) + 1000 * r for r in range(8)]
+    brick.connect(bases, tables)
+    base, offsets = brick.sim.connected[index(-1, 0, 0)]
+    neighbour = dd.brick_rank((0, 0, 1), bricks)
+    assert base == bases[neighbour]
+    assert offsets == list(tables[neighbour][index(1, 0, 0)])
+    assert brick.sim.mailboxes == {r: bases[r] for r in range(8)}
+
+
+def test_slab_bricks_have_two_neighbours_and_a_z_box():
+    cuts = dd.ball_brick_cuts(30.0, (1, 1, 4))
+    brick = dd.BrickDomain(FakeLib(), "relu_grid", 1000, 80, 1.0, (1, 1, 4), cuts, 2,
+                           4, face_capacity=500)
+    begun = brick.sim.begun
+    assert sorted(np.nonzero(begun["peers"] >= 0)[0]) == [4, 22]  # -z and +z faces
+    assert begun["first"][:2] == [0, 0] and begun["count"][:2] == [80, 80]
+    lo_cube = int(np.floor(cuts[2][1] - 1.5)) - 2 + 40
+    assert begun["first"][2] == lo_cube and begun["count"][2] < 80
+
+
 # ---- the decomposed run on one GPU ------------------------------------------------
 def match_cells(got, want, tol):
     from scipy.spatial import cKDTree

@@ -25,6 +25,8 @@ Limits (documented in DESIGN.md): Grid models without per-id property arrays
 ("relu_grid", "spring_grid", "epithelium"); cell identity is not tracked across
 migration; centre-of-mass fixing only.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -313,20 +315,39 @@ class BrickDomain:
 
     def connect_over_ipc(self, group=None):
         """Gather everybody's CUDA IPC handle and offsets (torch.distributed is
-        the plumbing), map the other ranks' allocations, connect."""
+        the plumbing), map the other ranks' allocations, connect. Raises
+        YallaError on EVERY rank if any rank cannot map a peer (no peer access,
+        IPC disabled in the container, ...), so that callers can fall back
+        together."""
+        from . import YallaError
         base, _, offsets = self.sim.dom_exchange()
         if self.world == 1:
             return self.connect([base], [offsets])
         mine = (self.lib.ipc_export(base), offsets)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
-        bases = []
+        bases, problem = [], None
+        if os.environ.get("YALLA_B200_NO_IPC"):  # exercise the callers' fallback
+            problem = "disabled by YALLA_B200_NO_IPC"
         for r, (handle, _) in enumerate(everyone):
-            if r == self.rank:
+            if r == self.rank or problem:
                 bases.append(base)
-            else:
+                continue
+            try:
                 bases.append(self.lib.ipc_import(handle))
                 self.mapped.append(bases[-1])
+            except YallaError as error:
+                problem = str(error)
+                break
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        fine = torch.tensor([0 if problem else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(fine, op=dist.ReduceOp.MIN, group=group)
+        if int(fine.item()) == 0:
+            for mapped in self.mapped:
+                self.lib.ipc_release(mapped)
+            self.mapped = []
+            raise YallaError("CUDA IPC between the ranks is not available: "
+                             + (problem or "another rank could not map a peer"))
         self.connect(bases, [table for _, table in everyone])
         dist.barrier(group=group)
 
