@@ -84,6 +84,41 @@ struct Dd_mailboxes {  // every rank's mailbox, mapped here (kernel argument)
     Dd_mailbox* of_rank[DD_MAX_RANKS];
 };
 
+// Per-cell arrays of the model that travel with the cells (kernel argument):
+// every one migrates with its cell and is re-stored with it; those the pairwise
+// functor reads of a NEIGHBOUR (a cell type, ...) also come with the ghosts.
+constexpr int DD_MAX_EXTRAS = 8;
+
+struct Dd_extras {
+    int count;
+    unsigned* data[DD_MAX_EXTRAS];     // the model's array, n_max entries
+    unsigned* scratch[DD_MAX_EXTRAS];  // same size: target of the re-store
+    int words[DD_MAX_EXTRAS];          // 32-bit words per cell
+    int ghosts_too[DD_MAX_EXTRAS];
+};
+
+__device__ __forceinline__ void write_extras(
+    float* tail, const Dd_extras& extras, int i, bool migration)
+{
+    unsigned* out = reinterpret_cast<unsigned*>(tail);
+    for (int k = 0; k < extras.count; k++) {
+        if (!migration && !extras.ghosts_too[k]) continue;
+        const unsigned* src = extras.data[k] + size_t(i) * extras.words[k];
+        for (int w = 0; w < extras.words[k]; w++) *out++ = src[w];
+    }
+}
+
+__device__ __forceinline__ void read_extras(
+    const float* tail, const Dd_extras& extras, int at, bool migration)
+{
+    const unsigned* in = reinterpret_cast<const unsigned*>(tail);
+    for (int k = 0; k < extras.count; k++) {
+        if (!migration && !extras.ghosts_too[k]) continue;
+        unsigned* dst = extras.data[k] + size_t(at) * extras.words[k];
+        for (int w = 0; w < extras.words[k]; w++) dst[w] = *in++;
+    }
+}
+
 __device__ __forceinline__ void store_release_sys(unsigned* p, unsigned value)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(value)
@@ -368,9 +403,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
     const int* __restrict__ d_n_total, int n_max,
     const unsigned char* __restrict__ halo_flags,
     const int* __restrict__ tile_offsets, const int* __restrict__ totals,
-    int n_tiles, Halo_faces faces, unsigned char* __restrict__ flags_stay)
+    int n_tiles, Halo_faces faces, unsigned char* __restrict__ flags_stay,
+    Dd_extras extras, int record_floats)
 {
-    constexpr int W = Layout<Pt>::lanes + 3;
+    constexpr int W_BASE = Layout<Pt>::lanes + 3;
+    const int W = record_floats;
     constexpr int WARPS = SCAN_THREADS / 32;
     __shared__ unsigned short s_count[DD_LISTS][SELECT_SUB][WARPS];  // -> prefixes
     __shared__ int s_tile_prefix[DD_LISTS];
@@ -482,9 +519,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
             before += rank;  // (a migrating entry has exactly one bit)
             if (bit < 31 && mine) {
                 const int at = s_tile_prefix[bit] + s_count[bit][u][warp_id] + rank;
-                if (at < s_capacity[bit])
-                    write_record(
-                        s_buffer[bit] + SLAB_HEADER + size_t(at) * W, P, v, i);
+                if (at < s_capacity[bit]) {
+                    float* record = s_buffer[bit] + SLAB_HEADER + size_t(at) * W;
+                    write_record(record, P, v, i);
+                    if (extras.count > 0)
+                        write_extras(record + W_BASE, extras, i, migration != 0);
+                }
             }
         }
         if (migration && q < n && mask[u] == 0) {
@@ -495,6 +535,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) dd_pack(const Step_ctl* ctl,
             store_pt(X_stay, at, X);
             v_stay[at] = v[i];
             flags_stay[at] = halo_flags_of(X.x, X.y, X.z, faces);
+            for (int k = 0; k < extras.count; k++) {  // re-stored via scratch
+                const int words = extras.words[k];
+                const unsigned* src = extras.data[k] + size_t(i) * words;
+                unsigned* dst = extras.scratch[k] + size_t(at) * words;
+                for (int w = 0; w < words; w++) dst[w] = src[w];
+            }
         }
     }
 }
@@ -568,9 +614,11 @@ __device__ __forceinline__ int dd_inbox_layout(
 // and set the total cell count. Order: by peer, then as ranked by the sender.
 template<typename Pt>
 __global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
-    float3* v, Dd_inboxes in, int n_max, int* d_n)
+    float3* v, Dd_inboxes in, int n_max, int* d_n, Dd_extras extras,
+    int record_floats)
 {
-    constexpr int W = Layout<Pt>::lanes + 3;
+    constexpr int W_BASE = Layout<Pt>::lanes + 3;
+    const int W = record_floats;
     __shared__ int s_start[DD_MAX_PEERS + 1];
     const int n = ctl->n_owned;
     if (threadIdx.x == 0) dd_inbox_layout(in, n_max - n, s_start);
@@ -580,8 +628,9 @@ __global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
          r += gridDim.x * blockDim.x) {
         int p = 0;
         while (r >= s_start[p + 1]) p++;
-        read_record(in.buffer[p] + SLAB_HEADER + size_t(r - s_start[p]) * W, P, v,
-            n + r);
+        const float* record = in.buffer[p] + SLAB_HEADER + size_t(r - s_start[p]) * W;
+        read_record(record, P, v, n + r);
+        if (extras.count > 0) read_extras(record + W_BASE, extras, n + r, false);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *d_n = n + total;
@@ -594,9 +643,11 @@ __global__ void __launch_bounds__(256) dd_append_ghosts(Step_ctl* ctl, Pt* P,
 template<typename Pt>
 __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
     const int* __restrict__ n_stay_in, Dd_inboxes in, int n_max, Pt* X, float3* v,
-    int* new_count, Halo_faces faces, unsigned char* __restrict__ halo_flags)
+    int* new_count, Halo_faces faces, unsigned char* __restrict__ halo_flags,
+    Dd_extras extras, int record_floats)
 {
-    constexpr int W = Layout<Pt>::lanes + 3;
+    constexpr int W_BASE = Layout<Pt>::lanes + 3;
+    const int W = record_floats;
     __shared__ int s_start[DD_MAX_PEERS + 1];
     const int n_stay = *n_stay_in;
     if (threadIdx.x == 0) dd_inbox_layout(in, n_max - n_stay, s_start);
@@ -607,11 +658,47 @@ __global__ void __launch_bounds__(256) dd_merge(const Step_ctl* ctl,
         int p = 0;
         while (a >= s_start[p + 1]) p++;
         const int r = n_stay + a;
-        read_record(in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W, X, v, r);
+        const float* record = in.buffer[p] + SLAB_HEADER + size_t(a - s_start[p]) * W;
+        read_record(record, X, v, r);
+        if (extras.count > 0) read_extras(record + W_BASE, extras, r, true);
         const float* x = reinterpret_cast<const float*>(X + r);
         halo_flags[r] = halo_flags_of(x[0], x[1], x[2], faces);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = n_stay + arrivals;
+}
+
+// The registered arrays of the cells that stayed: scratch -> the model's arrays
+// (dd_pack could not re-store them in place).
+__global__ void __launch_bounds__(256) dd_restore_extras(
+    const int* __restrict__ n_stay_in, Dd_extras extras)
+{
+    const int n_stay = *n_stay_in;
+    for (int k = 0; k < extras.count; k++) {
+        const long long words = static_cast<long long>(n_stay) * extras.words[k];
+        for (long long w = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+             w < words; w += static_cast<long long>(gridDim.x) * blockDim.x)
+            extras.data[k][w] = extras.scratch[k][w];
+    }
+}
+
+// Between two steps the model may have appended cells (division) and bumped
+// *d_n: flag the new ones, then adopt the count as this brick's owned cells.
+template<typename Pt>
+__global__ void __launch_bounds__(256) dd_flag_new_cells(const Step_ctl* ctl,
+    const int* __restrict__ d_n, int n_max, const Pt* __restrict__ X,
+    Halo_faces faces, unsigned char* __restrict__ halo_flags)
+{
+    const int n = live_cells(d_n, n_max);
+    for (int i = ctl->n_owned + blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += gridDim.x * blockDim.x) {
+        const float* x = reinterpret_cast<const float*>(X + i);
+        halo_flags[i] = halo_flags_of(x[0], x[1], x[2], faces);
+    }
+}
+
+__global__ void dd_adopt_owned(Step_ctl* ctl, const int* d_n, int n_max)
+{
+    ctl->n_owned = live_cells(d_n, n_max);
 }
 
 // Global drift of a stage: publish {sum dX, n} of the owned cells to every
@@ -711,7 +798,9 @@ struct Domain_link {
     int peer_rank[DD_MAX_PEERS] = {};
     int peer_direction[DD_MAX_PEERS] = {};  // direction index 0..26 of peer p
     int capacity[DD_MAX_PEERS] = {};
-    int record_floats = 0;
+    int record_floats = 0;        // of a migration record (the widest)
+    int halo_record_floats = 0;   // of a ghost record
+    Dd_extras extras{};           // registered before begin()
 
     unsigned char* base = nullptr;  // this rank's exchange allocation
     size_t bytes = 0;
@@ -736,6 +825,16 @@ struct Domain_link {
     float3* v_new = nullptr;  // the corrector's velocities, until re-stored
     bool flags_valid = false;             // false until a kernel has written them
     bool permute = true;
+    // the model appends cells between steps (division): every step starts by
+    // adopting them (set with the first registered array; may be set by hand)
+    bool grows = false;
+    // halo rounds: the push runs on its own stream while the brick's stream
+    // starts the grid build with the cells it owns (YALLA_B200_DD_OVERLAP=0:
+    // everything on one stream, as in round 1)
+    bool overlap = true;
+    cudaStream_t push_stream = nullptr;
+    cudaEvent_t packed = nullptr, pushed = nullptr;
+    bool push_pending = false;
 
     Halo_faces inset_faces() const
     {
@@ -749,13 +848,42 @@ struct Domain_link {
 
     static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
+    // A per-cell array of the model that has to travel with the cells; call
+    // before begin(). bytes_per_cell: a multiple of 4.
+    bool register_extra(void* d_array, int bytes_per_cell, bool ghosts_too)
+    {
+        if (active || extras.count >= DD_MAX_EXTRAS || bytes_per_cell % 4 != 0)
+            return false;
+        const int k = extras.count++;
+        extras.data[k] = static_cast<unsigned*>(d_array);
+        extras.words[k] = bytes_per_cell / 4;
+        extras.ghosts_too[k] = ghosts_too ? 1 : 0;
+        extras.scratch[k] = nullptr;
+        grows = true;
+        return true;
+    }
+
     void begin(int rank_, int world_, const Dd_region& region_,
-        const int* peer_ranks27, const int* capacity27, int record_floats_,
+        const int* peer_ranks27, const int* capacity27, int base_record_floats,
         int n_max)
     {
+        const Dd_extras registered = extras;
         release();
+        extras = registered;
         rank = rank_, world = world_, region = region_;
-        record_floats = record_floats_;
+        // records: the cell, its old velocity, then the registered arrays; an
+        // even number of floats keeps them 8-byte aligned
+        int all_words = 0, ghost_words = 0;
+        for (int k = 0; k < extras.count; k++) {
+            all_words += extras.words[k];
+            if (extras.ghosts_too[k]) ghost_words += extras.words[k];
+            YB_CUDA(cudaMalloc(&extras.scratch[k],
+                sizeof(unsigned) * size_t(extras.words[k]) * (n_max > 0 ? n_max : 1)));
+        }
+        record_floats = (base_record_floats + all_words + 1) & ~1;
+        halo_record_floats = (base_record_floats + ghost_words + 1) & ~1;
+        if (extras.count == 0)
+            record_floats = halo_record_floats = base_record_floats;
         region.n_peers = 0;
         for (int dir = 0; dir < 27; dir++) {
             if (dir == 13 || peer_ranks27[dir] < 0) continue;
@@ -815,6 +943,12 @@ struct Domain_link {
         YB_CUDA(cudaMalloc(&halo_flags, n_max > 0 ? n_max : 1));
         YB_CUDA(cudaMalloc(&v_new, sizeof(float3) * size_t(n_max > 0 ? n_max : 1)));
         flags_valid = false;
+        YB_CUDA(cudaStreamCreateWithFlags(&push_stream, cudaStreamNonBlocking));
+        YB_CUDA(cudaEventCreateWithFlags(&packed, cudaEventDisableTiming));
+        YB_CUDA(cudaEventCreateWithFlags(&pushed, cudaEventDisableTiming));
+        push_pending = false;
+        const char* overlap_env = getenv("YALLA_B200_DD_OVERLAP");
+        overlap = !(overlap_env && overlap_env[0] == '0');
         const char* env = getenv("YALLA_B200_SLAB_PERMUTE");
         permute = !(env && env[0] == '0');
         for (int q = 0; q < DD_ROUNDS; q++) epoch[q] = 0;
@@ -874,6 +1008,13 @@ struct Domain_link {
     void release()
     {
         if (!active) return;
+        cudaStreamSynchronize(push_stream);
+        cudaStreamDestroy(push_stream);
+        cudaEventDestroy(packed);
+        cudaEventDestroy(pushed);
+        push_stream = nullptr;
+        for (int k = 0; k < extras.count; k++) cudaFree(extras.scratch[k]);
+        extras = Dd_extras{};
         cudaFree(v_new);
         cudaFree(halo_flags);
         cudaFree(new_count);

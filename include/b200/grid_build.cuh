@@ -220,6 +220,32 @@ __global__ void __launch_bounds__(256) bin_cells(const int* __restrict__ d_n,
 }
 
 
+// The same pass over a part of the cells of a decomposed tissue: part 0 = the
+// cells this domain owns (before the ghosts of the stage have arrived, *d_n is
+// not final then), part 1 = the ghosts behind them. Arrival numbers differ from
+// one pass over all cells, the cube order built from them does not (in-cube
+// order is by ascending index, see stable_rank).
+template<typename Pt>
+__global__ void __launch_bounds__(256) bin_cells_part(const int* __restrict__ d_n,
+    int n_max, const Pt* __restrict__ d_X, float cube_size, Grid_box box,
+    int* __restrict__ key, int* __restrict__ arrival, int* count, Step_ctl* ctl,
+    int part)
+{
+    const int n_owned = min(ctl->n_owned, n_max);
+    const int first = part == 0 ? 0 : n_owned;
+    const int last = part == 0 ? n_owned : live_cells(d_n, n_max);
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last;
+         i += gridDim.x * blockDim.x) {
+        const float* p = reinterpret_cast<const float*>(d_X + i);
+        const int c = cube_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), cube_size,
+            box, &ctl->out_of_grid);
+        key[i] = c;
+        arrival[i] = atomicAdd(count + c, 1);
+    }
+    if (part == 1 && blockIdx.x == 0 && threadIdx.x == 0) ctl->n_snapshot = last;
+}
+
+
 // ---- step 2: single-pass exclusive scan with decoupled look-back ------------
 // Tiles of SCAN_TILE bins; tile ids are handed out dynamically so a tile only
 // ever waits on tiles that are already running. A tile publishes

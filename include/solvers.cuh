@@ -513,6 +513,18 @@ public:
     // dom_step then runs whole Heun steps without the host ever waiting.
     yb::Domain_link dom;
 
+    // A per-cell array of the model (a Property's d_prop, curand states, ...)
+    // that has to travel with the cells of a decomposed tissue: it migrates
+    // with its cell, is re-stored with it when a migration round leaves the
+    // cells in cube order, and -- ghosts_too, for arrays the pairwise functor
+    // reads of a NEIGHBOUR, like a cell type -- comes along with the ghosts.
+    // Entries are bytes_per_cell (a multiple of 4) wide and indexed like d_X;
+    // register before dom_begin.
+    bool dom_register_array(void* d_array, int bytes_per_cell, bool ghosts_too)
+    {
+        return dom.register_extra(d_array, bytes_per_cell, ghosts_too);
+    }
+
     void dom_begin(int rank, int world, const float lo[3], const float hi[3],
         float halo, const int peer_ranks27[27], const int capacity27[27])
     {
@@ -524,8 +536,25 @@ public:
         dd_set_counts(0, 0);
     }
 
+    // Generic forces of a decomposed step must be capturable in the sense of
+    // capture_generic_forces: they only enqueue work on
+    // yb::current_stage()->stream and take the live count (owned cells + ghosts)
+    // from d_n on the device; the n they are handed is n_max. Between two steps
+    // the model may append cells behind the owned ones and bump *d_n (division):
+    // the next step adopts them.
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction>
-    void dom_step(float dt)
+    void dom_step(float dt, Generic_forces<Pt> gen_forces = no_gen_forces<Pt>)
+    {
+        if (yb::is_no_gen_forces(gen_forces))
+            dom_step_impl<pw_int, pw_friction, false>(dt, gen_forces);
+        else
+            dom_step_impl<pw_int, pw_friction, true>(dt, gen_forces);
+    }
+
+private:
+    template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
+        bool SEEDED>
+    void dom_step_impl(float dt, Generic_forces<Pt>& gen_forces)
     {
         assert(dom.active && dom.connected());
         // With lazy module loading the first launch of a kernel may wait for the
@@ -540,31 +569,59 @@ public:
             yb::load_kernel(yb::dd_wait);
             yb::load_kernel(yb::dd_append_ghosts<Pt>);
             yb::load_kernel(yb::dd_merge<Pt>);
+            yb::load_kernel(yb::dd_restore_extras);
+            yb::load_kernel(yb::bin_cells_part<Pt>);
+            yb::load_kernel(yb::dd_flag_new_cells<Pt>);
+            yb::load_kernel(yb::dd_adopt_owned);
+            yb::load_kernel(yb::zero_cells<Pt>);
             yb::load_kernel(yb::dd_allreduce_drift);
             yb::load_kernel(yb::slab_commit_count);
             yb::load_kernel(yb::predictor_step<Pt, false>);
             yb::load_kernel(yb::corrector_step<Pt>);
-            Computer<Pt>::template load_kernels<pw_int, pw_friction, false>();
+            Computer<Pt>::template load_kernels<pw_int, pw_friction, SEEDED>();
             return true;
         }();
         (void)loaded;
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        ++step_serial;
         dom_mark(-1);
+        if (dom.grows) {
+            // cells the model appended since the last step (division)
+            yb::dd_flag_new_cells<Pt><<<blocks, 256, 0, stream>>>(
+                d_ctl, d_n, n_max, d_X, dom.inset_faces(), dom.halo_flags);
+            yb::dd_adopt_owned<<<1, 1, 0, stream>>>(d_ctl, d_n, n_max);
+        }
         for (int stage = 0; stage < 2; stage++) {
             Pt* X_stage = stage == 0 ? d_X : d_X1;
             Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
-            dom_round(stage, X_stage, d_old_v);
-            yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(
-                d_ctl, X_stage, d_old_v, dom.inboxes(stage), n_max, d_n);
+            const bool binned = dom_round(stage, X_stage, d_old_v);
+            yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(d_ctl, X_stage,
+                d_old_v, dom.inboxes(stage), n_max, d_n, dom.extras,
+                dom.halo_record_floats);
+            if (binned) Computer<Pt>::bin_part(stream, d_n, X_stage, d_ctl, 1);
             dom_mark(2);
+            if (SEEDED) {
+                yb::zero_cells<Pt><<<blocks, 256, 0, stream>>>(d_n, n_max, dX_stage);
+                yb::Stage_context context{n_max, n_max, stream};
+                context.d_n_cells = d_n;
+                context.stage = stage;
+                context.capturing = false;
+                context.solver = this;
+                context.step_serial = step_serial;
+                context.eager_stream = stream;
+                context.hooks = nullptr;
+                yb::current_stage() = &context;
+                gen_forces(n_max, X_stage, dX_stage);
+                yb::current_stage() = nullptr;
+            }
             cudaEvent_t sweep_start = nullptr, sweep_stop = nullptr;
             if (profiling) {
                 YB_CUDA(cudaEventCreate(&sweep_start));
                 YB_CUDA(cudaEventCreate(&sweep_stop));
             }
-            Computer<Pt>::template pwints<pw_int, pw_friction, false>(stream, d_n,
+            Computer<Pt>::template pwints<pw_int, pw_friction, SEEDED>(stream, d_n,
                 X_stage, d_old_v, dX_stage, d_partials, max_sweep_ctas, stage,
-                yb::DRIFT_MEAN, 0, d_ctl, false, sweep_start);
+                yb::DRIFT_MEAN, 0, d_ctl, binned, sweep_start);
             if (profiling) {
                 YB_CUDA(cudaEventRecord(sweep_stop, stream));
                 sweep_events.emplace_back(sweep_start, sweep_stop);
@@ -590,12 +647,17 @@ public:
         dom_round(2, d_X1, dom.v_new);
         yb::dd_merge<Pt><<<yb::stride_grid(n_max / 16 + 1, 256, yb::sm_count()), 256,
             0, stream>>>(d_ctl, dom.n_stay, dom.inboxes(2), n_max, d_X, d_old_v,
-            dom.new_count, dom.inset_faces(), dom.halo_flags);
+            dom.new_count, dom.inset_faces(), dom.halo_flags, dom.extras,
+            dom.record_floats);
+        if (dom.extras.count > 0)
+            yb::dd_restore_extras<<<blocks, 256, 0, stream>>>(dom.n_stay, dom.extras);
         yb::slab_commit_count<<<1, 1, 0, stream>>>(d_ctl, dom.new_count, d_n);
         dom.flags_valid = true;
         dom_mark(2);
         YB_CUDA(cudaGetLastError());
     }
+
+public:
 
     // Extension: where a decomposed step spends its time, by CUDA events on the
     // stream while profile_sweeps is on. Milliseconds since the last read for
@@ -647,13 +709,21 @@ private:
     // one exchange round: what 0 / 1 = halo of X / X1, 2 = migration
     // (cells at P with velocities v; a migration round re-stores the cells that
     // stay in d_X / d_old_v)
-    void dom_round(int what, const Pt* P, const float3* v)
+    // Returns true if the cube ids of the owned cells were computed on the way
+    // (halo rounds: while the outboxes travel, see below).
+    bool dom_round(int what, const Pt* P, const float3* v)
     {
         const bool migration = what == 2;
         const unsigned epoch = ++dom.epoch[what];
+        const int width = migration ? dom.record_floats : dom.halo_record_floats;
         // a brick without neighbours has no halo; its migration round still
         // re-stores the cells in cube order
-        if (dom.region.n_peers == 0 && !migration) return;
+        if (dom.region.n_peers == 0 && !migration) return false;
+        // the local outboxes are free once the previous round's push has read them
+        if (dom.push_pending) {
+            YB_CUDA(cudaStreamWaitEvent(stream, dom.pushed, 0));
+            dom.push_pending = false;
+        }
         const float4* order =
             migration && dom.permute ? Computer<Pt>::dd_cube_order() : nullptr;
         // stage 0: flags from the last dd_merge (not before the first step);
@@ -671,16 +741,36 @@ private:
         yb::dd_pack<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl, P, v,
             dom.region, dom.local_out, migration, d_X, d_old_v, dom.n_stay, order,
             d_n, n_max, flags, dom.tile_counts, dom.totals, dom.n_tiles,
-            dom.inset_faces(), dom.halo_flags);
+            dom.inset_faces(), dom.halo_flags, dom.extras, width);
         dom_mark(migration ? 7 : 0);
+        bool binned = false;
         if (dom.region.n_peers > 0) {
-            yb::dd_push<<<dom.region.n_peers * yb::dd_push_ctas(), 256, 0,
-                stream>>>(dom.local_out, dom.out[what], dom.region.n_peers,
-                yb::dd_push_ctas(), dom.record_floats, dom.push_done, epoch);
+            const int push_grid = dom.region.n_peers * yb::dd_push_ctas();
+            if (!migration && dom.overlap) {
+                // Halo exchange overlapped with interior work: the push runs on
+                // a side stream (the neighbours' pushes arrive on theirs) while
+                // this stream starts the grid build of the stage with the cells
+                // it owns -- their cube ids and the per-cube counts. The ghosts
+                // are binned when they have arrived.
+                YB_CUDA(cudaEventRecord(dom.packed, stream));
+                YB_CUDA(cudaStreamWaitEvent(dom.push_stream, dom.packed, 0));
+                yb::dd_push<<<push_grid, 256, 0, dom.push_stream>>>(dom.local_out,
+                    dom.out[what], dom.region.n_peers, yb::dd_push_ctas(), width,
+                    dom.push_done, epoch);
+                YB_CUDA(cudaEventRecord(dom.pushed, dom.push_stream));
+                dom.push_pending = true;
+                Computer<Pt>::bin_part(stream, d_n, P, d_ctl, 0);
+                binned = true;
+            } else {
+                yb::dd_push<<<push_grid, 256, 0, stream>>>(dom.local_out,
+                    dom.out[what], dom.region.n_peers, yb::dd_push_ctas(), width,
+                    dom.push_done, epoch);
+            }
             dom_mark(6);
             yb::dd_wait<<<1, 32, 0, stream>>>(d_ctl, dom.inboxes(what), epoch);
             dom_mark(1);
         }
+        return binned;
     }
     void dom_mark(int phase)
     {
@@ -972,6 +1062,7 @@ protected:
     void index_ahead(
         cudaStream_t, const int*, const Pt*, const float3*, yb::Step_ctl*)
     {}
+    void bin_part(cudaStream_t, const int*, const Pt*, yb::Step_ctl*, int) {}
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,
         bool SEEDED>
@@ -1359,6 +1450,17 @@ protected:
                 d_old_v, sort.key, sort.offset, sort.slot_id, pos4, aux,
                 cube_sorted);
         }
+    }
+
+    // Decomposed tissues: the first pass of the build in two parts -- the owned
+    // cells (part 0, while the halos are in flight) and the ghosts (part 1);
+    // pwints() is then told that the cells are binned already.
+    void bin_part(cudaStream_t s, const int* d_n, const Pt* d_X,
+        yb::Step_ctl* d_ctl, int part)
+    {
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        yb::bin_cells_part<Pt><<<blocks, 256, 0, s>>>(d_n, n_max, d_X, cube_size,
+            box, sort.key, sort.arrival, sort.count, d_ctl, part);
     }
 
     // Which of the two equivalent build tails to use (b200/grid_build.cuh):

@@ -245,6 +245,15 @@ int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems);
 int yb_dom_begin(yb_sim* sim, int rank, int world, const float* lo3,
     const float* hi3, float halo, const int* peer_ranks27,
     const int* capacity27, const int* box_first3, const int* box_n3);
+/* Before yb_dom_begin: a per-cell device array of the caller (n_max entries of
+ * bytes_per_cell bytes, a multiple of 4, indexed like the cells) that travels
+ * with the cells -- it migrates with its cell and is re-stored with it, and
+ * with ghosts_too != 0 it also comes along with the ghost copies (entries
+ * n_owned.. of the array then hold the ghosts' values during a step). This is
+ * how Property<T> arrays, curand states and cell identities survive the
+ * decomposition (the typed models register their own; at most 8 arrays). */
+int yb_dom_register_array(yb_sim* sim, void* d_array, int bytes_per_cell,
+    int ghosts_too);
 int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,
     long long* offsets27x6_out);
 int yb_dom_connect(yb_sim* sim, int direction, void* d_peer_base,

@@ -1049,6 +1049,10 @@ int yb_dom_begin(yb_sim*, int, int, const float*, const float*, float,
 {
     return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
 }
+int yb_dom_register_array(yb_sim*, void*, int, int)
+{
+    return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");
+}
 int yb_dom_exchange(yb_sim*, void**, long long*, long long*)
 {
     return fail(YB_ENOSYS, "peer-memory decomposition needs the product library");

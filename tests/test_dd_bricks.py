@@ -220,3 +220,133 @@ def test_seeded_lattice_ball_is_the_same_tissue_however_it_is_cut(product):
     # density of an FCC lattice with nearest-neighbour distance d
     expected = np.sqrt(2.0) / d ** 3 * 4.0 / 3.0 * np.pi * radius ** 3
     assert abs(len(tissues[0]) - expected) < 0.02 * expected
+
+
+# ---- per-cell arrays of the model travel with the cells ------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("bricks", [(1, 1, 2), (1, 2, 2)])
+def test_registered_arrays_travel_with_their_cells(product, bricks):
+    """Every brick registers an identity tag (ghosts_too) and a three-word
+    payload (owned cells only). After steps with migration each cell must still
+    carry ITS tag and payload: the cell tagged k sits where cell k of the
+    single-domain run sits, so identity is tracked across the cuts."""
+    import torch
+    rng = np.random.default_rng(43)
+    n, steps, dt = 30_000, 6, 0.1
+    X = (workloads.lattice_ball(n, 0.8, rng) * 0.9).astype(np.float32)
+    gs = workloads.grid_size_for(n, 0.8) + 4
+    with product.sim("relu_grid", n, gs, 1.0) as sim:
+        sim.set_state(X)
+        sim.step(dt, steps)
+        want = sim.get_state()
+    world = bricks[0] * bricks[1] * bricks[2]
+    cuts = dd.ball_brick_cuts(float(np.max(np.linalg.norm(X, axis=1))), bricks)
+    tags = [torch.full((n,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    loads = [torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+             for _ in range(world)]
+    domains = [dd.BrickDomain(product, "relu_grid", n, gs, 1.0, bricks, cuts, rank,
+                              world, face_capacity=n,
+                              arrays=[(tags[rank].data_ptr(), 4, True),
+                                      (loads[rank].data_ptr(), 12, False)])
+               for rank in range(world)]
+    streams = [torch.cuda.Stream() for _ in domains]
+    for domain, stream in zip(domains, streams):
+        domain.sim.set_stream(stream.cuda_stream)
+    dd.connect_local(domains)
+    ids = np.arange(n, dtype=np.int32)
+    before = []
+    for rank, domain in enumerate(domains):
+        mine = domain.owns(X)
+        before.append(int(mine.sum()))
+        domain.set_cells(X[mine])
+        tags[rank][:before[-1]] = torch.as_tensor(ids[mine], device="cuda")
+        loads[rank][:before[-1]] = torch.as_tensor(X[mine] * 2 + 1, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        for domain in domains:
+            domain.step(dt)
+    torch.cuda.synchronize()
+    seen, after = [], []
+    for rank, domain in enumerate(domains):
+        owned, with_ghosts, problems = domain.counts()
+        assert problems == 0 and with_ghosts > owned
+        after.append(owned)
+        got = domain.owned_state()[0].cpu().numpy()
+        tag = tags[rank][:owned].cpu().numpy()
+        load = loads[rank][:owned].cpu().numpy()
+        assert tag.min() >= 0
+        assert np.max(np.abs(got - want[tag])) < 2e-5 * steps * np.max(np.abs(want))
+        assert np.array_equal(load, X[tag] * 2 + 1)
+        seen.append(tag)
+    for domain in domains:
+        domain.close()
+    assert before != after, "no cell migrated: the test is too tame"
+    assert np.array_equal(np.sort(np.concatenate(seen)), ids)
+
+
+@pytest.mark.gpu
+def test_growth_model_through_the_decomposed_step(product):
+    """The Po_cell growth model (Property arrays, counter reset as generic force,
+    curand division) run through yb_dom_step as a single brick: the migration
+    pass re-stores cells, types, counters and curand states in cube order every
+    step and adopts the daughters. Division off: cell by cell the same state,
+    types and neighbour counters as the plain model; division on: the first
+    round divides exactly the same mothers."""
+    rng = np.random.default_rng(44)
+    n = 20_000
+    X = workloads.polarized_ball(n, 0.75, rng, lattice=True).astype(np.float32)
+    types = workloads.shell_types(X)
+    gs = workloads.grid_size_for(n, 0.75, growth=2.0)
+    cuts = dd.ball_brick_cuts(float(np.max(np.linalg.norm(X[:, :3], axis=1))),
+                              (1, 1, 1))
+
+    def plain(rate, steps):
+        with product.sim("growth", 2 * n, gs, 1.0) as sim:
+            sim.set_param("prolif_rate", rate)
+            sim.set_param("seed", 5)
+            sim.set_ints("type", types)
+            sim.set_state(X)
+            sim.step(0.1, steps)
+            return (sim.get_state(), sim.get_ints("type"), sim.get_ints("mes_nbs"),
+                    sim.get_ints("epi_nbs"))
+
+    def decomposed(rate, steps):
+        domain = dd.BrickDomain(product, "growth", 2 * n, gs, 1.0, (1, 1, 1), cuts,
+                                0, 1, face_capacity=n)
+        dd.connect_local([domain])
+        domain.sim.set_param("prolif_rate", rate)
+        domain.sim.set_param("seed", 5)
+        domain.set_cells(X)
+        domain.sim.set_ints("type", types)
+        domain.step(0.1, steps)
+        owned, _, problems = domain.counts()
+        assert problems == 0
+        out = (domain.owned_state()[0].cpu().numpy(), domain.sim.get_ints("type"),
+               domain.sim.get_ints("mes_nbs"), domain.sim.get_ints("epi_nbs"))
+        assert len(out[0]) == owned == len(out[1])
+        domain.close()
+        return out
+
+    from scipy.spatial import cKDTree
+    want, got = plain(0.0, 4), decomposed(0.0, 4)
+    assert len(got[0]) == len(want[0]) == n
+    distance, index = cKDTree(want[0][:, :3]).query(got[0][:, :3], k=1)
+    assert len(np.unique(index)) == n and distance.max() < 1e-2
+    # (a pair that sits on the cut-off within rounding may be counted on one
+    # side in one run and on the other in the other: a handful of cells at most)
+    assert np.sum(np.abs(got[0] - want[0][index]).max(axis=1) > 1e-4) <= 5
+    assert np.array_equal(got[1], want[1][index])  # the type came along
+    for k in (2, 3):  # mesenchymal and epithelial neighbour counts
+        assert np.sum(got[k] != want[k][index]) <= 5
+    assert 0 < got[1].sum() < n and got[2].max() > 0 and got[3].max() > 0
+
+    want, got = plain(0.05, 1), decomposed(0.05, 1)
+    assert len(got[0]) == len(want[0]) > n
+    assert np.array_equal(np.sort(got[1]), np.sort(want[1]))
+    a = got[0][np.lexsort(got[0][:, :3].T[::-1])]
+    b = want[0][np.lexsort(want[0][:, :3].T[::-1])]
+    assert np.max(np.abs(a - b)) < 1e-4
+    # and it keeps growing, every cell finite, counters alive
+    got = decomposed(0.05, 8)
+    assert len(got[0]) > len(want[0]) and np.all(np.isfinite(got[0]))
+    assert got[2].max() > 0

@@ -98,6 +98,8 @@ SIGNATURES = {
                                     ctypes.c_float, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p]),
+    "yb_dom_register_array": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_int]),
     "yb_dom_exchange": (ctypes.c_int, [ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(ctypes.c_longlong),
@@ -407,6 +409,12 @@ class Sim:
             self.handle, rank, world, lo.ctypes.data, hi.ctypes.data, halo,
             peers.ctypes.data, caps.ctypes.data, first.ctypes.data,
             count.ctypes.data), "dom_begin")
+
+    def dom_register_array(self, d_array, bytes_per_cell, ghosts_too=False):
+        """A per-cell device array that travels with the cells (before dom_begin)."""
+        self.lib.check(self.lib.cdll.yb_dom_register_array(
+            self.handle, d_array, bytes_per_cell, 1 if ghosts_too else 0),
+            "dom_register_array")
 
     def dom_exchange(self):
         """-> (device address, bytes, offsets[27, 6]) of this rank's exchange

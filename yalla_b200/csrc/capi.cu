@@ -146,6 +146,10 @@ struct yb_sim {
     {
         return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
     }
+    virtual int dom_register_array(void*, int, int)
+    {
+        return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
+    }
     virtual int dom_exchange(void**, long long*, long long*)
     {
         return fail(YB_ENOSYS, "domain decomposition: product Grid models only");
@@ -573,6 +577,16 @@ struct Sim_base : yb_sim {
     {
         return fail(YB_ENOSYS, "domain decomposition needs a Grid model");
     }
+    int dom_register_array(void* d_array, int bytes_per_cell, int ghosts_too) override
+    {
+        if (d_array == nullptr || bytes_per_cell <= 0 || bytes_per_cell % 4 != 0)
+            return fail(YB_EINVAL, "bytes_per_cell must be a positive multiple of 4");
+        if (!cells.dom_register_array(d_array, bytes_per_cell, ghosts_too != 0))
+            return fail(YB_EINVAL,
+                "register arrays before yb_dom_begin, at most " +
+                    std::to_string(yb::DD_MAX_EXTRAS));
+        return YB_OK;
+    }
     int dom_exchange(void** base, long long* bytes, long long* offsets) override
     {
         const yb::Domain_link& dom = cells.dom;
@@ -882,6 +896,24 @@ struct Typed_sim : Sim_base<Pt, Grid_solver> {
     ~Typed_sim() override { unbind(); }
 #ifdef YALLA_B200
     void stream_changed() override { unbind(); }
+    // Decomposed: the type travels with the cells AND their ghost copies (the
+    // functors read the partner's type), the counters with the cells only.
+    virtual void register_model_arrays()
+    {
+        auto& cells = this->cells;
+        cells.dom_register_array(type.d_prop, sizeof(models::Cell_types), true);
+        cells.dom_register_array(n_mes_nbs.d_prop, sizeof(int), false);
+        cells.dom_register_array(n_epi_nbs.d_prop, sizeof(int), false);
+    }
+    int dom_begin(int rank, int world, const float* lo3, const float* hi3,
+        float halo, const int* peer_ranks27, const int* capacity27,
+        const int* box_first3, const int* box_n3) override
+    {
+        static_assert(sizeof(models::Cell_types) == 4, "4-byte cell types");
+        if (this->cells.dom.extras.count == 0) register_model_arrays();
+        return Base::dom_begin(rank, world, lo3, hi3, halo, peer_ranks27,
+            capacity27, box_first3, box_n3);
+    }
 #endif
     int set_ints(const std::string& name, const int* values, int n) override
     {
@@ -995,6 +1027,43 @@ struct Growth_sim : Typed_sim<Po_cell> {
                 d_n_at_launch);
         }
     }
+
+#ifdef YALLA_B200
+    // Decomposed (one brick of the tissue per instance): the curand states
+    // travel with the cells too; every brick seeds its own streams.
+    void register_model_arrays() override
+    {
+        Typed_sim<Po_cell>::register_model_arrays();
+        static_assert(sizeof(curandState) % 4 == 0, "curandState in words");
+        cells.dom_register_array(d_state, sizeof(curandState), false);
+    }
+    int dom_step(float dt, int n_steps) override
+    {
+        if (!cells.dom.active || !cells.dom.connected())
+            return fail(YB_EINVAL, "the domain is not connected to its neighbours");
+        const int n_max = cells.n_max;
+        if (!seeded) {
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, model_stream()>>>(
+                n_max, seed + 7919 * cells.dom.rank, d_state);
+            seeded = true;
+        }
+        bind();
+        auto reset_nbs = [this](const int n, const Po_cell* __restrict__ d_X,
+                             Po_cell* d_dX) { reset_counters(n); };
+        for (int k = 0; k < n_steps; k++) {
+            cells.dom_step<models::relu_w_epithelium, friction_w_neighbour<Po_cell>>(
+                dt, reset_nbs);
+            if (prolif_rate > 0) {
+                models::snapshot_count<<<1, 1, 0, model_stream()>>>(
+                    cells.d_n, d_n_at_launch);
+                models::proliferate<<<(n_max + 128 - 1) / 128, 128, 0,
+                    model_stream()>>>(prolif_rate, mean_dist, n_max, d_state,
+                    cells.d_X, cells.d_old_v, cells.d_n, d_n_at_launch);
+            }
+        }
+        return check_cuda("yb_dom_step");
+    }
+#endif
 
     int step(float dt) override
     {
@@ -1503,6 +1572,12 @@ int yb_dom_begin(yb_sim* sim, int rank, int world, const float* lo3,
 {
     return sim->dom_begin(rank, world, lo3, hi3, halo, peer_ranks27, capacity27,
         box_first3, box_n3);
+}
+
+int yb_dom_register_array(yb_sim* sim, void* d_array, int bytes_per_cell,
+    int ghosts_too)
+{
+    return sim->dom_register_array(d_array, bytes_per_cell, ghosts_too);
 }
 
 int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,

@@ -253,10 +253,16 @@ class BrickDomain:
     memory over NVLink, ordered by flags the kernels themselves wait on."""
 
     def __init__(self, lib, model, n_max, grid_size, cube_size, bricks, cuts,
-                 rank, world, face_capacity, halo=1.5, local_grid=True):
+                 rank, world, face_capacity, halo=1.5, local_grid=True,
+                 arrays=()):
+        """arrays: (device address, bytes per cell, ghosts_too) of per-cell
+        arrays of the caller that travel with the cells (Sim.dom_register_array);
+        the typed models register their Property arrays themselves."""
         assert world == bricks[0] * bricks[1] * bricks[2]
         self.lib = lib
         self.sim = lib.sim(model, n_max, grid_size, cube_size)
+        for address, width, ghosts_too in arrays:
+            self.sim.dom_register_array(address, width, ghosts_too)
         self.lanes = self.sim.lanes
         self.n_max = n_max
         self.rank, self.world = rank, world
