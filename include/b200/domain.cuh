@@ -15,7 +15,9 @@
 //   [flags:   one word per (neighbour, round kind)]
 //   [inboxes: per (neighbour, round kind) a header and `capacity` records]
 //
-// Round kinds: 0 / 1 = halo of the predictor / corrector stage, 2 = migration.
+// Round kinds: 0 / 1 = halo of the predictor / corrector stage, 2 = migration,
+// 3 = survey (a halo of the positions ahead of the step, asked for by models
+// whose own kernels need the neighbours: dom_survey).
 // A round of rank A: a stable stream compaction (dd_tile_counts ->
 // dd_tile_offsets -> dd_pack, entry order preserved per destination) packs the
 // selected records into A's local outboxes, and dd_push streams every outbox
@@ -45,7 +47,8 @@ namespace yb {
 
 constexpr int DD_MAX_PEERS = 26;
 constexpr int DD_MAX_RANKS = 64;
-constexpr int DD_ROUNDS = 3;  // halo X, halo X1, migration
+constexpr int DD_ROUNDS = 4;  // halo X, halo X1, migration, survey (halo of X
+                              // ahead of the step, for the model's own kernels)
 
 // direction (dx, dy, dz) in {-1, 0, 1}^3 <-> index 0..26 (13 = the brick itself)
 inline int dd_direction_index(int dx, int dy, int dz)
@@ -701,6 +704,13 @@ __global__ void dd_adopt_owned(Step_ctl* ctl, const int* d_n, int n_max)
     ctl->n_owned = live_cells(d_n, n_max);
 }
 
+// End of a survey round: the ghosts are dropped again.
+__global__ void dd_drop_ghosts(Step_ctl* ctl, int* d_n)
+{
+    *d_n = ctl->n_owned;
+    ctl->n_ghosts = 0;
+}
+
 // Global drift of a stage: publish {sum dX, n} of the owned cells to every
 // rank, wait for everybody's, add in rank order, divide like operator/= would
 // (dtypes.cuh:204-208). One warp per 32 ranks; launched <<<1, DD_MAX_RANKS>>>.
@@ -812,7 +822,7 @@ struct Domain_link {
     unsigned char* local_base = nullptr;
     int* push_done = nullptr;
     Dd_mailboxes mailboxes{};
-    unsigned epoch[DD_ROUNDS] = {0, 0, 0};
+    unsigned epoch[DD_ROUNDS] = {};
     unsigned drift_epoch = 0;
 
     // scratch of the compaction: per list and tile, counts then offsets
@@ -965,15 +975,17 @@ struct Domain_link {
 
     // The peer in direction `dir` keeps my records in ITS inboxes for the
     // opposite direction: peer_base is its exchange allocation as mapped here,
-    // offsets6 = its {inbox_offset[q], flag_offset[q]} for direction 26 - dir.
-    bool connect(int dir, void* peer_base, const long long* offsets6)
+    // offsets = its {inbox_offset[q]..., flag_offset[q]...} (2 * DD_ROUNDS
+    // entries) for direction 26 - dir.
+    bool connect(int dir, void* peer_base, const long long* offsets)
     {
         const int p = peer_of_direction(dir);
         if (p < 0) return false;
         unsigned char* theirs = static_cast<unsigned char*>(peer_base);
         for (int q = 0; q < DD_ROUNDS; q++) {
-            out[q].buffer[p] = reinterpret_cast<float*>(theirs + offsets6[q]);
-            out[q].flag[p] = reinterpret_cast<unsigned*>(theirs + offsets6[3 + q]);
+            out[q].buffer[p] = reinterpret_cast<float*>(theirs + offsets[q]);
+            out[q].flag[p] =
+                reinterpret_cast<unsigned*>(theirs + offsets[DD_ROUNDS + q]);
             out[q].capacity[p] = capacity[p];
         }
         return true;

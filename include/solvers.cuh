@@ -497,7 +497,10 @@ public:
         yb::Step_ctl snapshot;
         YB_CUDA(cudaMemcpyAsync(&snapshot, d_ctl, sizeof(snapshot),
             cudaMemcpyDeviceToHost, stream));
-        get_d_n();  // waits for the stream
+        const int n_now = get_d_n();  // waits for the stream
+        // daughters appended since the last step are adopted by the next one
+        if (dom.active && dom.grows && n_now > snapshot.n_owned)
+            snapshot.n_owned = n_now;
         if (n_owned) *n_owned = snapshot.n_owned;
         // ghosts only live from a halo round to the end of its stage: report
         // how many the last round brought
@@ -536,6 +539,38 @@ public:
         dd_set_counts(0, 0);
     }
 
+    // Cells the model appended behind the owned ones since the last step
+    // (division) become owned cells of this brick. dom_step does this itself;
+    // models that survey the neighbourhood first (below) call it before.
+    void dom_adopt()
+    {
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        yb::dd_flag_new_cells<Pt><<<blocks, 256, 0, stream>>>(
+            d_ctl, d_n, n_max, d_X, dom.inset_faces(), dom.halo_flags);
+        yb::dd_adopt_owned<<<1, 1, 0, stream>>>(d_ctl, d_n, n_max);
+    }
+
+    // For model kernels that look at the neighbourhood of the cells BETWEEN
+    // steps (rewiring of protrusions, ...): an extra halo round of the current
+    // positions and of the registered ghosts_too arrays. Afterwards *d_n counts
+    // owned cells + ghosts and the ghosts sit behind the owned cells, as inside a
+    // stage; dom_end_survey() drops them again (call it before dom_step).
+    void dom_survey()
+    {
+        assert(dom.active && dom.connected());
+        const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
+        dom_round(3, d_X, d_old_v);
+        yb::dd_append_ghosts<Pt><<<blocks, 256, 0, stream>>>(d_ctl, d_X, d_old_v,
+            dom.inboxes(3), n_max, d_n, dom.extras, dom.halo_record_floats);
+        YB_CUDA(cudaGetLastError());
+    }
+    void dom_end_survey()
+    {
+        yb::dd_drop_ghosts<<<1, 1, 0, stream>>>(d_ctl, d_n);
+    }
+    // n_owned / n_ghosts of this brick, in device memory (for model kernels)
+    const yb::Step_ctl* dom_ctl() const { return d_ctl; }
+
     // Generic forces of a decomposed step must be capturable in the sense of
     // capture_generic_forces: they only enqueue work on
     // yb::current_stage()->stream and take the live count (owned cells + ghosts)
@@ -573,6 +608,7 @@ private:
             yb::load_kernel(yb::bin_cells_part<Pt>);
             yb::load_kernel(yb::dd_flag_new_cells<Pt>);
             yb::load_kernel(yb::dd_adopt_owned);
+            yb::load_kernel(yb::dd_drop_ghosts);
             yb::load_kernel(yb::zero_cells<Pt>);
             yb::load_kernel(yb::dd_allreduce_drift);
             yb::load_kernel(yb::slab_commit_count);
@@ -585,12 +621,7 @@ private:
         const int blocks = yb::stride_grid(n_max, 256, yb::sm_count());
         ++step_serial;
         dom_mark(-1);
-        if (dom.grows) {
-            // cells the model appended since the last step (division)
-            yb::dd_flag_new_cells<Pt><<<blocks, 256, 0, stream>>>(
-                d_ctl, d_n, n_max, d_X, dom.inset_faces(), dom.halo_flags);
-            yb::dd_adopt_owned<<<1, 1, 0, stream>>>(d_ctl, d_n, n_max);
-        }
+        if (dom.grows) dom_adopt();
         for (int stage = 0; stage < 2; stage++) {
             Pt* X_stage = stage == 0 ? d_X : d_X1;
             Pt* dX_stage = stage == 0 ? d_dX : d_dX1;
@@ -606,7 +637,9 @@ private:
                 context.d_n_cells = d_n;
                 context.stage = stage;
                 context.capturing = false;
-                context.solver = this;
+                // (no solver identity: indices of ghosts differ between the
+                // stages, so nothing a force builds in stage 0 holds in stage 1)
+                context.solver = nullptr;
                 context.step_serial = step_serial;
                 context.eager_stream = stream;
                 context.hooks = nullptr;
@@ -729,7 +762,7 @@ private:
         // stage 0: flags from the last dd_merge (not before the first step);
         // stage 1: from the predictor just now
         const unsigned char* flags =
-            (what == 1 || (what == 0 && dom.flags_valid)) ? dom.halo_flags : nullptr;
+            (what == 1 || (what != 2 && dom.flags_valid)) ? dom.halo_flags : nullptr;
         const int n_lists = dom.region.n_peers + (order != nullptr ? 1 : 0);
         yb::dd_tile_counts<Pt><<<dom.n_tiles, yb::SCAN_THREADS, 0, stream>>>(d_ctl,
             P, dom.region, migration, order, d_n, n_max, flags, dom.tile_counts,
@@ -746,7 +779,7 @@ private:
         bool binned = false;
         if (dom.region.n_peers > 0) {
             const int push_grid = dom.region.n_peers * yb::dd_push_ctas();
-            if (!migration && dom.overlap) {
+            if (what < 2 && dom.overlap) {
                 // Halo exchange overlapped with interior work: the push runs on
                 // a side stream (the neighbours' pushes arrive on theirs) while
                 // this stream starts the grid build of the stage with the cells

@@ -229,10 +229,11 @@ int yb_slab_counts(yb_sim* sim, int* n_owned, int* n_total, int* problems);
  *                   holds. box_first3 / box_n3: the cubes of the global grid
  *                   this brick can touch (box_n3[0] <= 0: the whole grid).
  *  yb_dom_exchange  device address and size of this rank's exchange allocation
- *                   and, per direction d, the byte offsets of its three
- *                   inboxes and three flag words (offsets27x6_out[6 d + q],
- *                   -1 without a neighbour). Other processes map the
- *                   allocation with yb_ipc_export / yb_ipc_import.
+ *                   and, per direction d, the byte offsets of its four
+ *                   inboxes (halo of either Heun stage, migration, survey) and
+ *                   four flag words: offsets_out[YB_DOM_OFFSETS d + q], -1
+ *                   without a neighbour. Other processes map the allocation
+ *                   with yb_ipc_export / yb_ipc_import.
  *  yb_dom_connect   the neighbour in `direction` keeps this rank's records at
  *                   d_peer_base (its allocation as mapped here) + the offsets
  *                   IT reported for the opposite direction, 26 - direction.
@@ -254,10 +255,11 @@ int yb_dom_begin(yb_sim* sim, int rank, int world, const float* lo3,
  * decomposition (the typed models register their own; at most 8 arrays). */
 int yb_dom_register_array(yb_sim* sim, void* d_array, int bytes_per_cell,
     int ghosts_too);
+#define YB_DOM_OFFSETS 8 /* entries per direction in the offset tables */
 int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,
-    long long* offsets27x6_out);
+    long long* offsets_out /* [27 * YB_DOM_OFFSETS] */);
 int yb_dom_connect(yb_sim* sim, int direction, void* d_peer_base,
-    const long long* peer_offsets6);
+    const long long* peer_offsets /* [YB_DOM_OFFSETS] */);
 int yb_dom_connect_mailbox(yb_sim* sim, int rank, void* d_peer_base);
 int yb_dom_seed_lattice_ball(yb_sim* sim, float radius, float dist_to_nb,
     float jitter, unsigned long long seed, int* n_out);

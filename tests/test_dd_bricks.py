@@ -57,8 +57,8 @@ class FakeSim:
                           halo=halo, peers=np.array(peers), caps=np.array(caps),
                           first=list(first), count=list(count))
 
-    def dom_connect(self, direction, base, offsets6):
-        self.connected[direction] = (base, list(offsets6))
+    def dom_connect(self, direction, base, offsets):
+        self.connected[direction] = (base, list(offsets))
 
     def dom_connect_mailbox(self, rank, base):
         self.mailboxes[rank] = base
@@ -94,7 +94,7 @@ def test_brick_layout_of_a_corner_brick():
     assert begun["first"] == [32 - 4, 0, 32 - 4] and begun["count"] == [36, 36, 36]
     # connecting: every neighbour's table is read at the OPPOSITE direction
     bases = list(range(100, 108))
-    tables = [np.arange(27 * 6).reshape(27, 6) + 1000 * r for r in range(8)]
+    tables = [np.arange(27 * 8).reshape(27, 8) + 1000 * r for r in range(8)]
     brick.connect(bases, tables)
     base, offsets = brick.sim.connected[index(-1, 0, 0)]
     neighbour = dd.brick_rank((0, 0, 1), bricks)
@@ -350,3 +350,74 @@ def test_growth_model_through_the_decomposed_step(product):
     got = decomposed(0.05, 8)
     assert len(got[0]) > len(want[0]) and np.all(np.isfinite(got[0]))
     assert got[2].max() > 0
+
+
+@pytest.mark.gpu
+def test_branching_growth_through_the_decomposed_step(product):
+    """configs[3] (branching cell, division, one protrusion per cell rewired
+    every step) as a single brick: links are kept as cell identities
+    (b200/brick_links.cuh), resolved to indices for the rewiring kernel and for
+    link_forces, and travel with the cells through the migration pass. The first
+    rewiring must produce exactly the links of the plain model; afterwards the
+    run keeps every link resolvable and grows at the plain model's rate."""
+    rng = np.random.default_rng(45)
+    n = 30_000
+    X = np.zeros((n, 7), dtype=np.float32)
+    X[:, :5] = workloads.polarized_ball(n, 0.75, rng, lattice=True, noise=0.0)
+    X[:, 5:] = rng.random((n, 2)).astype(np.float32) * 0.2
+    types = workloads.shell_types(X)
+    X[types == 0, 3:5] = 0
+    gs = workloads.grid_size_for(n, 0.75, growth=2.0)
+    cuts = dd.ball_brick_cuts(float(np.max(np.linalg.norm(X[:, :3], axis=1))),
+                              (1, 1, 1))
+
+    def plain(rate, steps):
+        with product.sim("branching_growth", 2 * n, gs, 1.0) as sim:
+            for name, value in (("seed", 9), ("mes_rate", rate), ("epi_rate", rate)):
+                sim.set_param(name, value)
+            sim.set_ints("type", types)
+            sim.set_state(X)
+            sim.step(0.1, steps)
+            return sim.get_state(), sim.get_links()
+
+    def decomposed(rate, steps):
+        domain = dd.BrickDomain(product, "branching_growth", 2 * n, gs, 1.0,
+                                (1, 1, 1), cuts, 0, 1, face_capacity=n, halo=2.5)
+        dd.connect_local([domain])
+        for name, value in (("seed", 9), ("mes_rate", rate), ("epi_rate", rate)):
+            domain.sim.set_param(name, value)
+        domain.set_cells(X)
+        domain.sim.set_ints("type", types)
+        domain.step(0.1, steps)
+        owned, _, problems = domain.counts()
+        assert problems == 0
+        out = (domain.owned_state()[0].cpu().numpy(), domain.sim.get_ints("identity"),
+               domain.sim.get_ints("partner"),
+               int(domain.sim.get_ints("unresolved_links")[0]))
+        assert len(out[0]) == owned == len(out[1]) == len(out[2])
+        domain.close()
+        return out
+
+    want_X, want_links = plain(0.0, 1)
+    got_X, identity, partner, unresolved = decomposed(0.0, 1)
+    assert unresolved == 0 and np.array_equal(np.sort(identity), np.arange(n))
+    live = want_links[:, 0] != want_links[:, 1]
+    assert live.sum() > 0.02 * (types == 0).sum()
+    # the plain model's link of cell a sits at index a
+    assert np.array_equal(want_links[live, 0], np.nonzero(live)[0])
+    expected = np.where(live, want_links[:n, 1], np.arange(n))
+    assert np.array_equal(partner, expected[identity])
+    assert np.max(np.abs(got_X - want_X[identity])) < 1e-4
+
+    want_X, _ = plain(0.01, 12)
+    got_X, identity, partner, unresolved = decomposed(0.01, 12)
+    assert unresolved == 0 and len(np.unique(identity)) == len(identity) > n
+    assert np.all(np.isfinite(got_X))
+    assert abs(len(got_X) - len(want_X)) < 0.02 * len(want_X)
+    linked = np.mean(partner != identity)
+    assert linked > 0.02
+    # both ends of every link are cells of the tissue, a protrusion's length apart
+    where = {int(g): k for k, g in enumerate(identity)}
+    ends = np.array([where[int(p)] for p in partner])
+    length = np.linalg.norm(got_X[:, :3] - got_X[ends, :3], axis=1)
+    assert length.max() < 3.0

@@ -31,6 +31,8 @@ _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_float_p = ctypes.POINTER(ctypes.c_float)
 
 # name -> (restype, argtypes); mirrors include/yalla_b200.h one to one
+DOM_OFFSETS = 8  # YB_DOM_OFFSETS of include/yalla_b200.h
+
 SIGNATURES = {
     "yb_build_info": (ctypes.c_char_p, []),
     "yb_last_error": (ctypes.c_char_p, []),
@@ -417,17 +419,18 @@ class Sim:
             "dom_register_array")
 
     def dom_exchange(self):
-        """-> (device address, bytes, offsets[27, 6]) of this rank's exchange
-        allocation: per direction the offsets of 3 inboxes and 3 flag words."""
+        """-> (device address, bytes, offsets[27, DOM_OFFSETS]) of this rank's exchange
+        allocation: per direction the offsets of 4 inboxes and 4 flag words."""
         base, size = ctypes.c_void_p(), ctypes.c_longlong()
-        offsets = np.zeros((27, 6), dtype=np.int64)
+        offsets = np.zeros((27, DOM_OFFSETS), dtype=np.int64)
         self.lib.check(self.lib.cdll.yb_dom_exchange(
             self.handle, ctypes.byref(base), ctypes.byref(size),
             offsets.ctypes.data), "dom_exchange")
         return base.value, size.value, offsets
 
-    def dom_connect(self, direction, peer_base, peer_offsets6):
-        offsets = np.ascontiguousarray(peer_offsets6, dtype=np.int64)
+    def dom_connect(self, direction, peer_base, peer_offsets):
+        offsets = np.ascontiguousarray(peer_offsets, dtype=np.int64)
+        assert offsets.size == DOM_OFFSETS
         self.lib.check(self.lib.cdll.yb_dom_connect(
             self.handle, direction, peer_base, offsets.ctypes.data), "dom_connect")
 

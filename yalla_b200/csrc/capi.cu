@@ -14,6 +14,9 @@
 #include <vector>
 
 #include "models.cuh"
+#ifdef YALLA_B200
+#include "b200/brick_links.cuh"
+#endif
 
 #include "yalla_b200.h"
 
@@ -593,24 +596,26 @@ struct Sim_base : yb_sim {
         if (!dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
         *base = dom.base;
         *bytes = static_cast<long long>(dom.bytes);
-        for (int q = 0; q < 27 * 6; q++) offsets[q] = -1;
+        constexpr int R = yb::DD_ROUNDS;
+        static_assert(2 * R == YB_DOM_OFFSETS, "yalla_b200.h: YB_DOM_OFFSETS");
+        for (int q = 0; q < 27 * 2 * R; q++) offsets[q] = -1;
         for (int p = 0; p < dom.region.n_peers; p++)
-            for (int q = 0; q < yb::DD_ROUNDS; q++) {
-                offsets[dom.peer_direction[p] * 6 + q] =
+            for (int q = 0; q < R; q++) {
+                offsets[dom.peer_direction[p] * 2 * R + q] =
                     static_cast<long long>(dom.inbox_offset[p][q]);
-                offsets[dom.peer_direction[p] * 6 + 3 + q] =
+                offsets[dom.peer_direction[p] * 2 * R + R + q] =
                     static_cast<long long>(dom.flag_offset[p][q]);
             }
         return YB_OK;
     }
     int dom_connect(int direction, void* peer_base,
-        const long long* peer_offsets6) override
+        const long long* peer_offsets) override
     {
         if (!cells.dom.active) return fail(YB_EINVAL, "yb_dom_begin first");
-        for (int q = 0; q < 6; q++)
-            if (peer_offsets6[q] < 0)
+        for (int q = 0; q < 2 * yb::DD_ROUNDS; q++)
+            if (peer_offsets[q] < 0)
                 return fail(YB_EINVAL, "the peer has no inbox for this direction");
-        if (!cells.dom.connect(direction, peer_base, peer_offsets6))
+        if (!cells.dom.connect(direction, peer_base, peer_offsets))
             return fail(YB_EINVAL, "no neighbour in this direction");
         return YB_OK;
     }
@@ -1224,6 +1229,93 @@ struct Branching_growth_sim : Typed_sim<models::Cell> {
         }
     }
 
+#ifdef YALLA_B200
+    // ---- decomposed (b200/brick_links.cuh) --------------------------------------
+    // One brick of the tissue per instance. Cells carry an identity and keep
+    // their protrusion as the identity of the partner; both travel with the
+    // cells and their ghost copies. Per iteration: adopt the daughters, survey
+    // the neighbourhood (extra halo round), rewire with the example's kernel on
+    // a Link array resolved over owned + ghost cells, then the decomposed Heun
+    // step whose generic force resolves the links again for each stage's ghosts.
+    yb::Brick_links brick_links;
+    void register_model_arrays() override
+    {
+        Typed_sim<models::Cell>::register_model_arrays();
+        brick_links.allocate(cells.n_max, models::prots_per_cell);
+        cells.dom_register_array(brick_links.identity, sizeof(int), true);
+        cells.dom_register_array(brick_links.partner,
+            sizeof(int) * models::prots_per_cell, true);
+    }
+    int get_ints(const std::string& name, int* values, int capacity) override
+    {
+        if (name != "identity" && name != "partner" && name != "unresolved_links")
+            return Typed_sim<models::Cell>::get_ints(name, values, capacity);
+        if (brick_links.identity == nullptr)
+            return fail(YB_EINVAL, "identities exist in decomposed runs only");
+        const int n = cells.get_d_n();  // waits for the model's stream
+        if (name == "unresolved_links") {
+            if (capacity < 1) return fail(YB_EINVAL, "capacity < 1");
+            cudaMemcpy(values, brick_links.diagnostics, sizeof(int),
+                cudaMemcpyDeviceToHost);
+            return check_cuda("get_ints");
+        }
+        const int per_cell = name == "partner" ? models::prots_per_cell : 1;
+        if (n * per_cell > capacity) return fail(YB_EINVAL, "capacity < n");
+        cudaMemcpy(values,
+            name == "partner" ? brick_links.partner : brick_links.identity,
+            sizeof(int) * size_t(n) * per_cell, cudaMemcpyDeviceToHost);
+        return check_cuda("get_ints");
+    }
+    int dom_step(float dt, int n_steps) override
+    {
+        if (!cells.dom.active || !cells.dom.connected())
+            return fail(YB_EINVAL, "the domain is not connected to its neighbours");
+        const int n_max = cells.n_max;
+        const cudaStream_t s = model_stream();
+        const int n_links_max = n_max * models::prots_per_cell;
+        if (!seeded) {
+            const int offset = 7919 * cells.dom.rank;  // own streams per brick
+            setup_rand_states<<<(n_max + 128 - 1) / 128, 128, 0, s>>>(
+                n_max, seed + offset, d_state);
+            setup_rand_states<<<(n_links_max + 128 - 1) / 128, 128, 0, s>>>(
+                n_links_max, seed + 1 + offset, protrusions.d_state);
+            seeded = true;
+        }
+        this->bind();
+        brick_links.rank = cells.dom.rank;
+        auto intercalation = [this](const int n, const models::Cell* __restrict__ d_X,
+                                 models::Cell* d_dX) {
+            reset_counters(n);
+            brick_links.resolve(yb::current_stage()->stream, cells.dom_ctl(),
+                cells.d_n, protrusions.d_link, protrusions.d_n);
+            link_forces(protrusions, d_X, d_dX);
+        };
+        for (int k = 0; k < n_steps; k++) {
+            brick_links.issue(s, cells.dom_ctl(), cells.d_n);
+            cells.dom_adopt();
+            cells.dom_survey();
+            brick_links.resolve(
+                s, cells.dom_ctl(), cells.d_n, protrusions.d_link, protrusions.d_n);
+            grid.stream = s;
+            grid.build_live(cells.d_n, cells.d_X, models::r_protrusion);
+            models::update_protrusions<<<(n_links_max + 32 - 1) / 32, 32, 0, s>>>(
+                cells.d_n, grid.d_grid, cells.d_X, protrusions.d_state,
+                protrusions.d_link);
+            brick_links.commit(s, cells.dom_ctl(), protrusions.d_link);
+            cells.dom_end_survey();
+            cells.dom_step<models::epi_turing_mes_noturing,
+                friction_w_neighbour<models::Cell>>(dt, intercalation);
+            if (mes_rate > 0 || epi_rate > 0) {
+                models::snapshot_count<<<1, 1, 0, s>>>(cells.d_n, d_n_at_launch);
+                models::proliferate_branching<<<(n_max + 128 - 1) / 128, 128, 0,
+                    s>>>(mes_rate, epi_rate, mean_dist, n_max, d_state, cells.d_X,
+                    cells.d_old_v, cells.d_n, d_n_at_launch);
+            }
+        }
+        return check_cuda("yb_dom_step");
+    }
+#endif
+
     int step(float dt) override
     {
         const int n_max = cells.n_max;
@@ -1581,15 +1673,15 @@ int yb_dom_register_array(yb_sim* sim, void* d_array, int bytes_per_cell,
 }
 
 int yb_dom_exchange(yb_sim* sim, void** d_base_out, long long* bytes_out,
-    long long* offsets27x6_out)
+    long long* offsets27xK_out)
 {
-    return sim->dom_exchange(d_base_out, bytes_out, offsets27x6_out);
+    return sim->dom_exchange(d_base_out, bytes_out, offsets27xK_out);
 }
 
 int yb_dom_connect(yb_sim* sim, int direction, void* d_peer_base,
-    const long long* peer_offsets6)
+    const long long* peer_offsets)
 {
-    return sim->dom_connect(direction, d_peer_base, peer_offsets6);
+    return sim->dom_connect(direction, d_peer_base, peer_offsets);
 }
 
 int yb_dom_connect_mailbox(yb_sim* sim, int rank, void* d_peer_base)

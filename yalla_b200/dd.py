@@ -311,7 +311,7 @@ class BrickDomain:
 
     def connect(self, bases, offsets):
         """bases[r]: rank r's exchange allocation as an address valid in this
-        process; offsets[r]: its [27, 6] table (Sim.dom_exchange)."""
+        process; offsets[r]: its [27, 8] table (Sim.dom_exchange)."""
         for d in range(27):
             r = int(self.peer_ranks[d])
             if r >= 0:
