@@ -440,6 +440,83 @@ def run_decomposed(steps, warmup, spec, workload, rank, local_rank, world,
     return line
 
 
+def run_decomposed_model(steps, warmup, workload, rank, local_rank, world):
+    """BASELINE.json configs[3] on `world` GPUs: ONE tissue of the typed model
+    (branching cell + Property arrays + division + protrusions rewired per step)
+    cut into bricks -- strong scaling, the cell count is fixed. Property arrays,
+    cell identities and links travel with the cells (Solution::dom_register_array,
+    include/b200/brick_links.cuh). Returns the record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from yalla_b200 import dd
+
+    spec = WORKLOADS[workload]
+    X, types, gs = make_state(spec, seed=1000)  # the same tissue on every rank
+    halo = 2.5 if spec["model"] == "branching_growth" else 1.5
+    bricks = dd.brick_grid_for(world)
+    radius = float(np.max(np.linalg.norm(X[:, :3], axis=1)))
+    density = np.sqrt(2.0) / spec["d"] ** 3
+    across = sorted(bricks)
+    face_cells = int(np.pi * radius ** 2 / (across[0] * across[1]) * halo * density)
+    n_faces = sum(1 for b in bricks if b > 1) * (2 if max(bricks) > 2 else 1)
+    share = spec["n_max"] / spec["n"]
+    n_max = int(len(X) / world * share * 1.05) + n_faces * int(face_cells * 1.3) + 8192
+    lib = yb.product()
+    domain = dd.BrickDomain(lib, spec["model"], n_max, gs, 1.0, bricks,
+                            dd.ball_brick_cuts(radius, bricks), rank, world,
+                            face_capacity=int(face_cells * 1.4) + 8192, halo=halo)
+    domain.connect_over_ipc()
+    for key, value in spec["params"].items():
+        domain.sim.set_param(key, value)
+    mine = domain.owns(X)
+    domain.set_cells(X[mine])
+    domain.sim.set_ints("type", types[mine])
+    del X
+    dt = spec["dt"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    domain.step(dt, warmup)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n_before = domain.counts()[0]
+    start.record()
+    domain.step(dt, steps)
+    stop.record()
+    barrier()
+    ms = start.elapsed_time(stop)
+    n_after, with_ghosts, problems = domain.counts()
+    unresolved = 0
+    if spec["model"] == "branching_growth":
+        unresolved = int(domain.sim.get_ints("unresolved_links")[0])
+    stats = torch.tensor([ms, 0.5 * (n_before + n_after), float(n_after),
+                          float(with_ghosts - n_after), float(problems),
+                          float(unresolved)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        worst = stats.clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        ms = float(worst[0])
+    barrier()
+    domain.close()
+    if rank != 0:
+        return None
+    return {"value": float(stats[1]) * steps / (ms * 1e-3), "unit": "cell-updates/s",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+            "scaling": "strong", "cells_end": int(stats[2]),
+            "ghost_cells": int(stats[3]), "problems": int(stats[4]),
+            "unresolved_link_stages": int(stats[5]),
+            "config": {"workload": workload, "model": spec["model"],
+                       "cells_start": spec["n"], "bricks": list(bricks),
+                       "halo": halo, "dt": dt, "grid_size": gs,
+                       "parallelism": "bricks %dx%dx%d over peer memory; Property "
+                       "arrays, cell identities and links travel with the cells"
+                       % bricks}}
+
+
 def time_reference(lib, spec, X, types, gs, steps, warmup, repeats):
     """Best of `repeats` runs of the reference build; every run starts from the
     same state as the product arm (state and types reloaded, `warmup` untimed
@@ -767,6 +844,19 @@ def main():
             if rank == 0:
                 print(f"bench: decomposed record failed: {error!r}", file=sys.stderr)
                 decomposed = dict(decomposed or {}, error=repr(error))
+        # configs[3] on the same N GPUs: the 10 M-cell branching tissue with
+        # division and protrusions, one tissue cut into bricks (strong scaling)
+        if os.environ.get("YALLA_BENCH_CONFIG3", "1") != "0":
+            try:
+                model_record = run_decomposed_model(
+                    5, 3, "branching_growth_10M", rank, local_rank, world)
+                if rank == 0:
+                    decomposed = dict(decomposed or {}, configs3=model_record)
+            except Exception as error:
+                if rank == 0:
+                    print(f"bench: decomposed configs[3] failed: {error!r}",
+                          file=sys.stderr)
+                    decomposed = dict(decomposed or {}, configs3={"error": repr(error)})
 
     if rank != 0:
         if use_dist:

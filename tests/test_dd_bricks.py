@@ -411,7 +411,9 @@ def test_branching_growth_through_the_decomposed_step(product):
 
     want_X, _ = plain(0.01, 12)
     got_X, identity, partner, unresolved = decomposed(0.01, 12)
-    assert unresolved == 0 and len(np.unique(identity)) == len(identity) > n
+    assert unresolved == 0
+    assert len(np.unique(identity)) == len(identity) > n, (
+        len(np.unique(identity)), len(identity))
     assert np.all(np.isfinite(got_X))
     assert abs(len(got_X) - len(want_X)) < 0.02 * len(want_X)
     linked = np.mean(partner != identity)

@@ -1290,8 +1290,10 @@ struct Branching_growth_sim : Typed_sim<models::Cell> {
                 cells.d_n, protrusions.d_link, protrusions.d_n);
             link_forces(protrusions, d_X, d_dX);
         };
+        // identities: for all cells before the first step, for the daughters
+        // right after every division (so that they can be read back with them)
+        if (!brick_links.issued) brick_links.issue(s, cells.dom_ctl(), cells.d_n);
         for (int k = 0; k < n_steps; k++) {
-            brick_links.issue(s, cells.dom_ctl(), cells.d_n);
             cells.dom_adopt();
             cells.dom_survey();
             brick_links.resolve(
@@ -1310,6 +1312,7 @@ struct Branching_growth_sim : Typed_sim<models::Cell> {
                 models::proliferate_branching<<<(n_max + 128 - 1) / 128, 128, 0,
                     s>>>(mes_rate, epi_rate, mean_dist, n_max, d_state, cells.d_X,
                     cells.d_old_v, cells.d_n, d_n_at_launch);
+                brick_links.issue(s, cells.dom_ctl(), cells.d_n);
             }
         }
         return check_cuda("yb_dom_step");
