@@ -77,6 +77,9 @@ WORKLOADS = {
                                  n_max=12_582_912, d=0.75, dt=0.2,
                                  params={"mes_rate": 0.006, "epi_rate": 0.006,
                                          "seed": 4}, typed=True),
+    # Gabriel_solver: the relu force on Gabriel neighbours only
+    "gabriel_1M": dict(model="relu_gabriel", n=1_000_000, n_max=1_000_000, d=0.8,
+                       dt=0.1, params={}, typed=False),
     "growth_100k": dict(model="growth", n=100_000, n_max=262_144, d=0.75,
                         dt=0.2, params={"prolif_rate": 0.006, "mean_dist": 0.75,
                                         "seed": 2}, typed=True),
@@ -195,7 +198,7 @@ class ClockSampler:
 # 8(d): counted from the SASS of the reference build; bending-type functors
 # include their MUFU expansions). The growth functor bends only epithelium-
 # epithelium pairs, a thin shell of the tissue.
-FUNCTOR_LANE_INSTR = {"relu_grid": 12, "spring_grid": 8, "protrusions": 12,
+FUNCTOR_LANE_INSTR = {"relu_grid": 12, "relu_gabriel": 12, "spring_grid": 8, "protrusions": 12,
                       "growth": 20, "epithelium": 250, "branching": 270,
                       "branching_growth": 270}
 

@@ -1327,13 +1327,7 @@ public:
         YB_CUDA(cudaMalloc(
             &aux, cells * yb::Layout<Pt>::aux_vec4 * sizeof(float4)));
         YB_CUDA(cudaMalloc(&cube_sorted, cells * sizeof(int)));
-        if (split_sweep()) {
-            nb_stride = (n_max > 0 ? n_max : 1) + 31 & ~31;
-            YB_CUDA(cudaMalloc(
-                &nb, size_t(nb_stride) * yb::LIST_MAX * sizeof(int)));
-            YB_CUDA(cudaMalloc(&nb_count, size_t(nb_stride) * sizeof(int)));
-            YB_CUDA(cudaMalloc(&nb_order, size_t(nb_stride) + yb::SWEEP_THREADS));
-        }
+        if (split_sweep()) allocate_lists();
         // scratch of the state-carrying build tail only
         if (carry_state())
             YB_CUDA(cudaMalloc(&staged,
@@ -1354,6 +1348,16 @@ public:
     }
 
 protected:
+    // neighbour lists of list_cubes (the split sweep, the Gabriel solver)
+    void allocate_lists()
+    {
+        if (nb != nullptr) return;
+        nb_stride = (n_max > 0 ? n_max : 1) + 31 & ~31;
+        YB_CUDA(cudaMalloc(&nb, size_t(nb_stride) * yb::LIST_MAX * sizeof(int)));
+        YB_CUDA(cudaMalloc(&nb_count, size_t(nb_stride) * sizeof(int)));
+        YB_CUDA(cudaMalloc(&nb_order, size_t(nb_stride) + yb::SWEEP_THREADS));
+    }
+
     // everything the stage kernels get by value
     yb::Graph_key graph_key() const
     {

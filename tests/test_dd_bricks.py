@@ -52,6 +52,10 @@ class FakeSim:
         self.connected = {}
         self.mailboxes = {}
 
+    def dom_register_array(self, address, width, ghosts_too):
+        assert self.begun is None, "arrays are registered before dom_begin"
+        self.arrays = getattr(self, "arrays", []) + [(address, width, ghosts_too)]
+
     def dom_begin(self, rank, world, lo, hi, halo, peers, caps, first, count):
         self.begun = dict(rank=rank, world=world, lo=np.array(lo), hi=np.array(hi),
                           halo=halo, peers=np.array(peers), caps=np.array(caps),
@@ -101,6 +105,29 @@ def test_brick_layout_of_a_corner_brick():
     assert base == bases[neighbour]
     assert offsets == list(tables[neighbour][index(1, 0, 0)])
     assert brick.sim.mailboxes == {r: bases[r] for r in range(8)}
+
+
+def test_model_arrays_are_registered_before_the_domain_begins():
+    cuts = dd.ball_brick_cuts(30.0, (1, 1, 2))
+    brick = dd.BrickDomain(FakeLib(), "relu_grid", 1000, 80, 1.0, (1, 1, 2), cuts, 1,
+                           2, face_capacity=500, halo=2.5,
+                           arrays=[(4096, 4, True), (8192, 48, False)])
+    assert brick.sim.arrays == [(4096, 4, True), (8192, 48, False)]
+    begun = brick.sim.begun
+    assert begun["halo"] == 2.5
+    # a wider halo widens the box of cubes the brick can touch
+    lo_cube = int(np.floor(cuts[2][0] - 2.5)) - 2 + 40
+    assert begun["first"][2] == lo_cube
+
+
+def test_offset_tables_cover_four_round_kinds():
+    import yalla_b200 as yb
+    header = open(yb.PRODUCT_LIB.replace("yalla_b200/_lib/libyalla_b200.so",
+                                         "include/yalla_b200.h")).read()
+    assert f"#define YB_DOM_OFFSETS {yb.DOM_OFFSETS}" in header
+    domain = open(yb.PRODUCT_LIB.replace("yalla_b200/_lib/libyalla_b200.so",
+                                         "include/b200/domain.cuh")).read()
+    assert f"constexpr int DD_ROUNDS = {yb.DOM_OFFSETS // 2};" in domain
 
 
 def test_slab_bricks_have_two_neighbours_and_a_z_box():
