@@ -610,7 +610,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
         const float4* __restrict__ pos4, const int* __restrict__ cube_sorted,
         const int* __restrict__ offset, float cube_size, Grid_box box,
         int* __restrict__ nb, int* __restrict__ nb_count,
-        unsigned char* __restrict__ nb_order, int nb_stride, Step_ctl* ctl)
+        unsigned char* __restrict__ nb_order, int nb_stride, Step_ctl* ctl,
+        int overflow_at)
 {
     constexpr int SWEEP_STAGE_CAP = List_config::stage_cap;
     constexpr int SWEEP_LIST_CAP = List_config::list_cap;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, List_config::min_ctas)
             }
         }
         if (live) nb_count[k] = n_listed;
-        if (n_listed > LIST_MAX) ctl->list_overflow = 1;
+        if (n_listed > overflow_at) ctl->list_overflow = 1;  // <= LIST_MAX
 
 #if YB_INTERACT_BALANCE
         // Which cell of the chunk thread q of interact_lists takes: the cells

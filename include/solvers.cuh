@@ -1562,7 +1562,7 @@ protected:
                                  max_ctas),
                 yb::SWEEP_THREADS, yb::List_config::smem, s>>>(d_n, n_max, pos4,
                 cube_sorted, sort.offset, cube_size, box, nb, nb_count,
-                nb_order, nb_stride, d_ctl);
+                nb_order, nb_stride, d_ctl, yb::LIST_MAX);
             yb::interact_lists<Pt, pw_int, pw_friction, SEEDED>
                 <<<persistent_ctas(
                        prepare_interact<pw_int, pw_friction, SEEDED>(),

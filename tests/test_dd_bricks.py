@@ -450,3 +450,69 @@ def test_branching_growth_through_the_decomposed_step(product):
     ends = np.array([where[int(p)] for p in partner])
     length = np.linalg.norm(got_X[:, :3] - got_X[ends, :3], axis=1)
     assert length.max() < 3.0
+
+
+@pytest.mark.gpu
+def test_registering_arrays_reports_misuse_and_empty_bricks_work(product):
+    """Edge cases of the travelling arrays: widths that are not whole words, too
+    many arrays, registration after the domain began -- all refused with an
+    error; a brick that owns no cell at all (the tissue lies entirely in its
+    neighbour) still exchanges, and a tissue that drifts into it arrives with
+    its arrays."""
+    import torch
+    import yalla_b200 as yb
+    n, gs = 4000, 40
+    tag = torch.zeros(n, dtype=torch.int32, device="cuda")
+    with product.sim("relu_grid", n, gs, 1.0) as sim:
+        with pytest.raises(yb.YallaError, match="multiple of 4"):
+            sim.dom_register_array(tag.data_ptr(), 6)
+        for _ in range(8):
+            sim.dom_register_array(tag.data_ptr(), 4)
+        with pytest.raises(yb.YallaError, match="at most 8"):
+            sim.dom_register_array(tag.data_ptr(), 4)
+    with product.sim("relu_tile", 64) as sim:
+        with pytest.raises(yb.YallaError, match="Grid model"):
+            sim.dom_begin(0, 1, [-np.inf] * 3, [np.inf] * 3, 1.5,
+                          np.full(27, -1, np.int32), np.zeros(27, np.int32),
+                          [0, 0, 0], [0, 0, 0])
+
+    # two bricks cut at z = 6: all cells start below the cut
+    rng = np.random.default_rng(46)
+    X = workloads.lattice_ball(n, 0.8, rng).astype(np.float32) * 0.9
+    X[:, 2] += 6.0 - X[:, 2].max() - 0.05
+    cuts = [[], [], [6.0]]
+    tags = [torch.full((n,), -1, dtype=torch.int32, device="cuda") for _ in range(2)]
+    domains = [dd.BrickDomain(product, "relu_grid", n, gs, 1.0, (1, 1, 2), cuts, rank,
+                              2, face_capacity=n,
+                              arrays=[(tags[rank].data_ptr(), 4, True)])
+               for rank in range(2)]
+    with pytest.raises(yb.YallaError, match="before yb_dom_begin"):
+        domains[0].sim.dom_register_array(tag.data_ptr(), 4)
+    streams = [torch.cuda.Stream() for _ in domains]
+    for domain, stream in zip(domains, streams):
+        domain.sim.set_stream(stream.cuda_stream)
+    dd.connect_local(domains)
+    owned = [domain.owns(X) for domain in domains]
+    assert owned[0].all() and not owned[1].any()
+    for rank, domain in enumerate(domains):
+        domain.set_cells(X[owned[rank]])
+    tags[0][:n] = torch.arange(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(10):  # the squeezed ball expands across the cut
+        for domain in domains:
+            domain.step(0.1)
+    torch.cuda.synchronize()
+    counts = [domain.counts() for domain in domains]
+    assert all(c[2] == 0 for c in counts)
+    assert counts[0][0] + counts[1][0] == n and counts[1][0] > 0
+    with product.sim("relu_grid", n, gs, 1.0) as sim:
+        sim.set_state(X)
+        sim.step(0.1, 10)
+        want = sim.get_state()
+    for rank, domain in enumerate(domains):
+        got = domain.owned_state()[0].cpu().numpy()
+        ids = tags[rank][:counts[rank][0]].cpu().numpy()
+        assert ids.min() >= 0
+        assert np.max(np.abs(got - want[ids])) < 1e-3
+    for domain in domains:
+        domain.close()
