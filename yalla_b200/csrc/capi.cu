@@ -1246,6 +1246,12 @@ struct Branching_growth_sim : Typed_sim<models::Cell> {
         cells.dom_register_array(brick_links.partner,
             sizeof(int) * models::prots_per_cell, true);
     }
+    // a freshly loaded tissue gets fresh identities (and no links)
+    int slab_set_owned(const float* X, const float* v, int n_owned) override
+    {
+        brick_links.issued = false;
+        return Typed_sim<models::Cell>::slab_set_owned(X, v, n_owned);
+    }
     int get_ints(const std::string& name, int* values, int capacity) override
     {
         if (name != "identity" && name != "partner" && name != "unresolved_links")
