@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(GABRIEL_THREADS) gabriel_lists(
             for (int e = 0; e < listed; e++) {
                 const int q = __ldg(nb + size_t(e) * nb_stride + k);
                 const float4 pj = __ldg(pos4 + q);
-                const float dist =
-                    norm3df(me.x - pj.x, me.y - pj.y, me.z - pj.z);
+                const float dist = pair_distance(
+                    me.x - pj.x, me.y - pj.y, me.z - pj.z, q == k);
                 if (dist >= cube_size) continue;
                 nb_slot[n_nbs] = q;
                 nb_dist[n_nbs] = dist;

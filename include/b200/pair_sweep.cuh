@@ -220,6 +220,17 @@ __device__ __forceinline__ Pt assemble_pt(
     return X;
 }
 
+// |r| exactly as the reference computes it (norm3df), except that the self pair
+// -- r = 0, one entry of every cell's list -- does not drag its warp through
+// norm3df's out-of-range path (a divergent call for one lane in about 40 % of
+// the warp iterations): it is handed a unit vector and the result replaced by
+// the 0 norm3df would have returned.
+__device__ __forceinline__ float pair_distance(float rx, float ry, float rz, bool self)
+{
+    const float d = norm3df(self ? 1.f : rx, ry, rz);
+    return self ? 0.f : d;
+}
+
 template<typename Pt>
 __device__ __forceinline__ float3 velocity_of(
     const float4* __restrict__ aux_of_cell)
@@ -522,10 +533,11 @@ __global__ void __launch_bounds__(
                     const float4 pj = s_pos[at];
                     const Pt Xj = assemble_pt<Pt>(pj, aux_j);
                     const Pt rij = Xi - Xj;
-                    const float dist = norm3df(rij.x, rij.y, rij.z);
+                    const int j_id = __float_as_int(pj.w);
+                    const float dist =
+                        pair_distance(rij.x, rij.y, rij.z, j_id == my_id);
                     if (dist >= cube_size) continue;
 
-                    const int j_id = __float_as_int(pj.w);
                     F += pw_int(Xi, rij, dist, my_id, j_id);
                     const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
                     sum_friction += friction;
@@ -902,10 +914,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, YB_INTERACT_CTAS) interact_list
 #endif
 
             const Pt rij = Xi - partner_pt<Pt>(now);
-            const float dist = norm3df(rij.x, rij.y, rij.z);
+            const int j_id = __float_as_int(now.pos.w);
+            const float dist = pair_distance(rij.x, rij.y, rij.z, j_id == my_id);
             if (dist >= cube_size) continue;
 
-            const int j_id = __float_as_int(now.pos.w);
             F += pw_int(Xi, rij, dist, my_id, j_id);
             const float friction = pw_friction(Xi, rij, dist, my_id, j_id);
             sum_friction += friction;
