@@ -149,10 +149,11 @@ __global__ void __launch_bounds__(GABRIEL_THREADS) sweep_gabriel(
 // own expression (norm3df) within a relative 1e-5 of the threshold, so the
 // decisions are the reference's. A cell with more than LIST_MAX listed
 // candidates sends the whole stage to sweep_gabriel (launched behind).
-// Measured at 1 M cells (profiles/r02_gabriel_ab.log): 1.64 ms per step against
-// 1.77 with sweep_gabriel alone and 8.1 with the reference's build. Keeping the
-// per-cell arrays in shared memory instead of thread-local memory was tried:
-// 40 KB per 64-thread CTA leave 10 warps per SM, 2.21 ms.
+// Measured at 1 M cells (profiles/r02_gabriel_ab.log), 8 CTAs per SM: 1.64 ms
+// per step against 1.77 with sweep_gabriel alone and 8.1 with the reference's
+// build; with grids sized by occupancy 1.42 against 1.31 -- see use_lists.
+// Keeping the per-cell arrays in shared memory instead of thread-local memory
+// was tried: 40 KB per 64-thread CTA leave 10 warps per SM, 2.21 ms.
 template<typename Pt, Pt (*pw_int)(Pt, Pt, float, int, int),
     float (*pw_friction)(Pt, Pt, float, int, int), bool SEEDED>
 __global__ void __launch_bounds__(GABRIEL_THREADS) gabriel_lists(
@@ -292,12 +293,15 @@ public:
         this->allocate_lists();
     }
 
-    // Extension: false = the round-1 kernel that scans the 27 cubes itself
-    // (kept as the fallback for crowded tissues and for A/B timing;
-    // YALLA_B200_GABRIEL_LISTS=0 sets it for every solver).
+    // Extension: true = take the candidates from the staged neighbour lists
+    // (list_cubes + gabriel_lists) instead of scanning the 27 cubes in
+    // sweep_gabriel; YALLA_B200_GABRIEL_LISTS=1 sets it for every solver. Off by
+    // default: once both kernels got grids sized by occupancy (20 CTAs of 64
+    // threads per SM instead of 8) the plain kernel was the faster one at 1 M
+    // cells, 1.31 against 1.42 ms per step (profiles/r02_gabriel_ab.log).
     bool use_lists = [] {
         const char* env = getenv("YALLA_B200_GABRIEL_LISTS");
-        return !(env && env[0] == '0');
+        return env && env[0] == '1';
     }();
 
 protected:
@@ -314,7 +318,24 @@ protected:
     int prepare()
     {
         Grid_computer<Pt>::prepare_list();  // attributes: not inside a capture
-        return 8;
+        // The per-cell arrays live in thread-local memory, so the kernels wait
+        // for the L1 most of the time: as many 64-thread CTAs as the registers
+        // allow (the ncu capture of the first version, sized for 8 CTAs = 16
+        // warps per SM, showed 24 % issue-slot use with long-scoreboard stalls).
+        static const int ctas_per_sm = [] {
+            int lists = 0, plain = 0;
+            YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lists,
+                yb::gabriel_lists<Pt, pw_int, pw_friction, SEEDED>,
+                yb::GABRIEL_THREADS, 0));
+            YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plain,
+                yb::sweep_gabriel<Pt, pw_int, pw_friction, SEEDED>,
+                yb::GABRIEL_THREADS, 0));
+            int ctas = lists < plain ? lists : plain;
+            const char* cap = getenv("YALLA_B200_GABRIEL_CTAS");
+            if (cap && cap[0] && atoi(cap) > 0) ctas = atoi(cap);
+            return ctas < 1 ? 1 : (ctas > 32 ? 32 : ctas);
+        }();
+        return ctas_per_sm;
     }
 
     template<Pairwise_interaction<Pt> pw_int, Pairwise_friction<Pt> pw_friction,

@@ -297,7 +297,7 @@ public:
         fresh.scan_epoch = 1;
         YB_CUDA(cudaMemcpy(
             d_ctl, &fresh, sizeof(fresh), cudaMemcpyHostToDevice));
-        max_sweep_ctas = yb::sm_count() * 16;
+        max_sweep_ctas = yb::sm_count() * 32;
         YB_CUDA(cudaMalloc(&d_partials, 3 * max_sweep_ctas * sizeof(float)));
         YB_CUDA(cudaStreamCreateWithFlags(
             &capture_stream, cudaStreamNonBlocking));
